@@ -1,0 +1,16 @@
+"""b200clip — B200-native (sm_100a) hot path for rom1504/clip-retrieval.
+
+Two paths, each behind the reference's own Python seam:
+  * search: `B200FlatIndex` / `B200IVFFlatIndex` — the FAISS index object of
+    clip_retrieval/clip_back.py:362 (`search`, `search_and_reconstruct`, `ntotal`, `d`, `nprobe`);
+  * embed:  `load_clip` / `ClipMapper` — clip_retrieval/clip_inference/mapper.py:16-78.
+Everything numeric runs in the CUDA library `lib/libb200clip.so` (C ABI in include/b200clip.h);
+there is no CPU fallback: importing works without a GPU, calling compute without one raises.
+"""
+from ._lib import lib, B200Error, library_path, launch_count  # noqa: F401
+from .index import B200FlatIndex, B200IVFFlatIndex, SynthSpec, load_index, merge_shard_results  # noqa: F401
+
+__all__ = [
+    "lib", "B200Error", "library_path", "launch_count",
+    "B200FlatIndex", "B200IVFFlatIndex", "SynthSpec", "load_index", "merge_shard_results",
+]

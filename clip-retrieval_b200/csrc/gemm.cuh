@@ -1,0 +1,256 @@
+// tcgen05 GEMM core of the embed path:
+//   C[M,N] = epilogue(A[M,K] · W[N,K]^T)     A, W bf16 row-major (both "K-major"), fp32 accumulate.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (W) boxes, 128B swizzle,
+//               into a 4-stage shared-memory ring guarded by full/empty mbarriers;
+//   warp 1      allocates the 512 TMEM columns and issues tcgen05.mma (128 x BN x 16 per instruction,
+//               4 per stage); tcgen05.commit releases ring slots and publishes finished accumulators;
+//   warps 2..5  epilogue: tcgen05.ld of the fp32 accumulator (each thread owns one output row),
+//               + bias, activation, + residual, bf16 pack, 16-byte global stores.
+// Two accumulator stages (2 x BN columns of TMEM) let the epilogue of tile i overlap the main loop
+// of tile i+1.  Tiles are walked in groups of 16 row-blocks x all column-blocks so the activation
+// rows of a group stay in L2 while the weights (a few MB) are re-read from L2, not HBM.
+// Roofline: tensor pipe; 2*M*N*K flops per launch.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_GROUP_M = 16;
+
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU = 2 };
+
+struct GemmEpilogue {
+  const float* bias = nullptr;              // [N] fp32 or null
+  const __nv_bfloat16* residual = nullptr;  // added after the activation, or null
+  int64_t res_ld = 0;                       // residual leading dimension (elements)
+  int res_row_mod = 0;                      // > 0: residual row = res_row_off + row % res_row_mod
+  int res_row_off = 0;
+  __nv_bfloat16* out = nullptr;
+  int64_t out_ld = 0;
+  int out_group = 0;                        // > 0: out row = (row / g) * (g + 1) + 1 + row % g  (cls slot)
+  int act = ACT_NONE;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN * 4 + 256 + 1024;  // ring + bias + barriers + align slack
+  static constexpr int TMEM_COLS = 2 * BN;                                         // 512 or 256
+};
+
+__device__ __forceinline__ void gemm_tile_coords(int tile, int mb, int nb, int& m_blk, int& n_blk) {
+  const int per_group = GEMM_GROUP_M * nb;
+  const int g = tile / per_group;
+  const int first_m = g * GEMM_GROUP_M;
+  const int gsize = min(GEMM_GROUP_M, mb - first_m);
+  const int r = tile - g * per_group;
+  m_blk = first_m + r % gsize;
+  n_blk = r / gsize;
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_QUICK_GELU) {
+    // x * sigmoid(1.702 x)
+    return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  } else if (act == ACT_GELU) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  }
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                         int K, GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = base;
+  uint8_t* sB = base + STAGES * Cfg::A_BYTES;
+  float* s_bias = reinterpret_cast<float*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + BN);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb = (M + GEMM_BM - 1) / GEMM_BM, nb = (N + BN - 1) / BN, kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles = mb * nb;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; s++) {
+        ptx::mbar_init(&full[s], 1);
+        ptx::mbar_init(&empty[s], 1);
+      }
+      for (int a = 0; a < 2; a++) {
+        ptx::mbar_init(&tfull[a], 1);
+        ptx::mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
+        for (int kbi = 0; kbi < kb; kbi++) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kbi * GEMM_BK, m_blk * GEMM_BM);
+          ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kbi * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(GEMM_BM, BN, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kbi = 0; kbi < kb; kbi++) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; k++) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzled row
+            ptx::umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int et = (warp - 2) * 32 + lane;  // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
+      const int n0 = n_blk * BN;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int j = et; j < BN; j += 128) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      int64_t out_row = row;
+      if (ep.out_group > 0) out_row = (int64_t)(row / ep.out_group) * (ep.out_group + 1) + 1 + row % ep.out_group;
+      int64_t res_row = row;
+      if (ep.res_row_mod > 0) res_row = ep.res_row_off + row % ep.res_row_mod;
+      __nv_bfloat16* out_ptr = ep.out + out_row * ep.out_ld + n0;
+      const __nv_bfloat16* res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        ptx::tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int col = c * 32 + g * 8;
+            if (n0 + col < N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r[g * 8 + j]) + s_bias[col + j], ep.act);
+              if (res_ptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr + col);
+                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z),
+                             dd = unpack_bf16x2(rr.w);
+                v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+                v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(out_ptr + col) = o;
+            }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// host side (gemm.cu)
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols);
+int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int M, int N, int K,
+                     const GemmEpilogue& ep, int sms, cudaStream_t st);
+// Pick the column-block width for a GEMM with N output columns (256, or 128 when N % 256 != 0 or the
+// grid would be under-filled).
+int gemm_pick_bn(int M, int N, int sms);
+
+}  // namespace b200

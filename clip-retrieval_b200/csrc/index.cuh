@@ -1,0 +1,46 @@
+// The index handle behind b200_index* (flat and IVF-Flat share the row store and the top-k tail).
+#pragma once
+#include "common.cuh"
+#include <mutex>
+#include <vector>
+
+struct b200_index {
+  int d = 0;
+  int device = 0;
+  int sms = 148;
+  int64_t ntotal = 0;
+  int64_t capacity = 0;     // rows allocated in `rows`
+  bool reserved = false;
+  __half* rows = nullptr;   // flat: insertion order.  IVF: list order after finalize.
+  int64_t id_base = 0;
+
+  // IVF-Flat
+  int nlist = 0;            // 0 = flat
+  int nprobe = 1;
+  __half* centroids = nullptr;      // [nlist, d] fp16
+  int64_t* list_offsets = nullptr;  // device [nlist + 1] (row offsets into `rows`)
+  uint32_t* row_ids = nullptr;      // device [ntotal]: local insertion id of the row at each slot
+  std::vector<int64_t> h_list_offsets;
+  int64_t nfinal = 0;               // rows already bucketed
+  __half* pending = nullptr;        // rows added but not yet bucketed (insertion order)
+  int64_t npending = 0, pending_cap = 0;
+  int64_t max_list = 0;
+
+  // scratch
+  void* ws[4] = {nullptr, nullptr, nullptr, nullptr};   // slot 0: scan internals; 1..3: callers
+  size_t ws_bytes[4] = {0, 0, 0, 0};
+  std::mutex mu;
+
+  // scan timing (CUDA events on the launching stream)
+  std::vector<cudaEvent_t> ev;   // pairs
+  int ev_used = 0;
+  int last_scan_launches = 0;
+};
+
+namespace b200 {
+int index_ws(b200_index* idx, int slot, size_t bytes, void** out);
+// Row scan + top-k of nq queries against rows [0, n) of `rows` (row-major fp16, d columns).
+// Writes, per query, k sorted keys (local row ids) into d_keys_out [nq, k].
+int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* d_q, int nq, int k,
+                   unsigned long long* d_keys_out, cudaStream_t st);
+}  // namespace b200

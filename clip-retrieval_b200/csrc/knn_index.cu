@@ -1,0 +1,392 @@
+// C ABI of the search path: the index object that replaces the FAISS index behind
+// KnnService.knn_search (reference clip_retrieval/clip_back.py:343-399; the FAISS calls are
+// load_index :589-596 and index.search_and_reconstruct :362).
+#include "index.cuh"
+#include "topk.cuh"
+#include <float.h>
+#include <algorithm>
+#include <new>
+
+namespace b200 {
+
+int decode_keys(const unsigned long long* keys, int64_t count, int64_t id_base, const uint32_t* slot_to_id, float* D,
+                int64_t* I, cudaStream_t st);
+template <typename OutT>
+int synth_rows(OutT* d_out, int64_t n, int d, int64_t row0, const b200_synth_spec* spec, cudaStream_t st);
+// IVF (knn_ivf.cu)
+int ivf_create(b200_index* idx, int nlist, const float* h_centroids);
+int ivf_finalize(b200_index* idx);
+int ivf_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec);
+int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned long long* d_keys, cudaStream_t st);
+int ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
+void ivf_free(b200_index* idx);
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = __float2half_rn(in[i]);
+}
+
+// Reconstruct: one warp per (query, rank); slot < 0 or key 0 -> all-ones bits (what FAISS leaves).
+__global__ void gather_rows_from_keys_kernel(const __half* __restrict__ rows, int d,
+                                             const unsigned long long* __restrict__ keys, int64_t count,
+                                             float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= count) return;
+  const unsigned long long key = keys[w];
+  float* o = out + w * d;
+  if (key == 0ull) {
+    for (int j = lane; j < d; j += 32) o[j] = __uint_as_float(0xffffffffu);
+  } else {
+    const __half* r = rows + (int64_t)key_id(key) * d;
+    for (int j = lane; j < d; j += 32) o[j] = __half2float(r[j]);
+  }
+}
+
+__global__ void gather_rows_from_slots_kernel(const __half* __restrict__ rows, int d,
+                                              const int64_t* __restrict__ ids, int64_t id_base, int64_t ntotal,
+                                              const uint32_t* __restrict__ id_to_slot, int64_t count,
+                                              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= count) return;
+  int64_t local = ids[w] - id_base;
+  float* o = out + w * d;
+  if (ids[w] < 0 || local < 0 || local >= ntotal) {
+    for (int j = lane; j < d; j += 32) o[j] = __uint_as_float(0xffffffffu);
+  } else {
+    if (id_to_slot) local = id_to_slot[local];
+    const __half* r = rows + local * d;
+    for (int j = lane; j < d; j += 32) o[j] = __half2float(r[j]);
+  }
+}
+
+// Merge G per-shard sorted candidate lists (score desc, global id asc) into one top-k per query.
+struct Cand {
+  uint32_t ord;
+  int64_t id;
+};
+__device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
+  return a.ord > b.ord || (a.ord == b.ord && a.id < b.id);
+}
+__global__ void __launch_bounds__(1024)
+merge_shards_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, int G, int nq, int k, int P,
+                    float* __restrict__ D, int64_t* __restrict__ I) {
+  extern __shared__ unsigned char smem_raw[];
+  uint32_t* ords = reinterpret_cast<uint32_t*>(smem_raw);
+  int64_t* ids = reinterpret_cast<int64_t*>(smem_raw + (size_t)P * 4 + ((P & 1) ? 4 : 0));
+  const int q = blockIdx.x;
+  const int M = G * k;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    uint32_t o = 0;
+    int64_t id = INT64_MAX;
+    if (i < M) {
+      const int g = i / k, j = i % k;
+      const int64_t src = ((int64_t)g * nq + q) * k + j;
+      const int64_t gid = Ig[src];
+      if (gid >= 0) { o = f32_to_ordered(Dg[src]); id = gid; }
+    }
+    ords[i] = o;
+    ids[i] = id;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        Cand a{ords[lo], ids[lo]}, b{ords[hi], ids[hi]};
+        if (cand_before(b, a) == up) {
+          ords[lo] = b.ord; ids[lo] = b.id;
+          ords[hi] = a.ord; ids[hi] = a.id;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool empty = ids[j] == INT64_MAX;
+    D[(int64_t)q * k + j] = empty ? -FLT_MAX : ordered_to_f32(ords[j]);
+    I[(int64_t)q * k + j] = empty ? -1 : ids[j];
+  }
+}
+
+static int ensure_capacity(b200_index* idx, int64_t need) {
+  if (need <= idx->capacity) return B200_OK;
+  int64_t cap = need;
+  if (!idx->reserved && idx->capacity > 0) cap = std::max<int64_t>(need, idx->capacity + idx->capacity / 2);
+  __half* nr = nullptr;
+  B200_CUDA(cudaMalloc((void**)&nr, (size_t)cap * idx->d * sizeof(__half)));
+  if (idx->rows) {
+    if (idx->ntotal > 0)
+      B200_CUDA(cudaMemcpy(nr, idx->rows, (size_t)idx->ntotal * idx->d * sizeof(__half), cudaMemcpyDeviceToDevice));
+    B200_CUDA(cudaFree(idx->rows));
+  }
+  idx->rows = nr;
+  idx->capacity = cap;
+  return B200_OK;
+}
+
+static int search_device_impl(b200_index* idx, const float* d_q, int nq, int k, float* d_D, int64_t* d_I, float* d_R,
+                              cudaStream_t st) {
+  B200_CHECK(nq >= 0 && k >= 1, B200_ERR_INVALID, "search: bad nq=%d k=%d", nq, k);
+  if (nq == 0) return B200_OK;
+  B200_CHECK(d_q && d_D && d_I, B200_ERR_INVALID, "search: null buffer");
+  B200_CHECK(((uintptr_t)d_q & 15) == 0, B200_ERR_INVALID, "search: query buffer must be 16-byte aligned");
+  idx->ev_used = 0;
+  idx->last_scan_launches = 0;
+  void* ws = nullptr;
+  B200_TRY(index_ws(idx, 1, (size_t)nq * k * 8, &ws));
+  unsigned long long* keys = (unsigned long long*)ws;
+  const uint32_t* slot_to_id = nullptr;
+  if (idx->nlist > 0) {
+    B200_TRY(ivf_finalize(idx));
+    B200_TRY(ivf_search_keys(idx, d_q, nq, k, keys, st));
+    slot_to_id = idx->row_ids;
+  } else {
+    B200_TRY(scan_topk_keys(idx, idx->rows, idx->ntotal, d_q, nq, k, keys, st));
+  }
+  B200_TRY(decode_keys(keys, (int64_t)nq * k, idx->id_base, slot_to_id, d_D, d_I, st));
+  if (d_R) {
+    const int64_t count = (int64_t)nq * k;
+    gather_rows_from_keys_kernel<<<(unsigned)((count + 7) / 8), 256, 0, st>>>(idx->rows, idx->d, keys, count, d_R);
+    B200_LAUNCH_OK();
+  }
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_index_create_flat(int d, int device, b200_index** out) {
+  B200_CHECK(out != nullptr, B200_ERR_INVALID, "create_flat: null out");
+  B200_CHECK(d > 0 && d % 8 == 0 && d <= 2048, B200_ERR_INVALID, "create_flat: d=%d must be a multiple of 8, <= 2048", d);
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  B200_CHECK(device >= 0 && device < ndev, B200_ERR_INVALID, "create_flat: device %d of %d", device, ndev);
+  b200_index* idx = new (std::nothrow) b200_index();
+  B200_CHECK(idx != nullptr, B200_ERR_OOM, "create_flat: host allocation failed");
+  idx->d = d;
+  idx->device = device;
+  idx->sms = sm_count(device);
+  *out = idx;
+  return B200_OK;
+}
+
+int b200_index_create_ivfflat(int d, int nlist, const float* h_centroids, int device, b200_index** out) {
+  B200_CHECK(nlist >= 1 && h_centroids != nullptr, B200_ERR_INVALID, "create_ivfflat: bad nlist/centroids");
+  B200_TRY(b200_index_create_flat(d, device, out));
+  DeviceGuard g(device);
+  int rc = ivf_create(*out, nlist, h_centroids);
+  if (rc != B200_OK) {
+    b200_index_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int b200_index_destroy(b200_index* idx) {
+  if (!idx) return B200_OK;
+  DeviceGuard g(idx->device);
+  cudaDeviceSynchronize();
+  if (idx->rows) cudaFree(idx->rows);
+  for (int i = 0; i < 4; i++)
+    if (idx->ws[i]) cudaFree(idx->ws[i]);
+  for (auto e : idx->ev) cudaEventDestroy(e);
+  ivf_free(idx);
+  delete idx;
+  return B200_OK;
+}
+
+int b200_index_reserve(b200_index* idx, int64_t n) {
+  B200_CHECK(idx && n >= 0, B200_ERR_INVALID, "reserve: bad argument");
+  DeviceGuard g(idx->device);
+  idx->reserved = true;
+  if (idx->nlist > 0) return B200_OK;  // IVF sizes its store at finalize
+  return ensure_capacity(idx, n);
+}
+
+static int add_rows(b200_index* idx, const void* rows, int64_t n, int on_device, bool f32) {
+  B200_CHECK(idx && (rows || n == 0) && n >= 0, B200_ERR_INVALID, "add: bad argument");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(idx->device);
+  const int d = idx->d;
+  __half* dst;
+  if (idx->nlist > 0) {
+    // IVF: stage in insertion order until finalize buckets them
+    const int64_t need = idx->npending + n;
+    if (need > idx->pending_cap) {
+      __half* np = nullptr;
+      B200_CUDA(cudaMalloc((void**)&np, (size_t)need * d * sizeof(__half)));
+      if (idx->pending) {
+        B200_CUDA(cudaMemcpy(np, idx->pending, (size_t)idx->npending * d * 2, cudaMemcpyDeviceToDevice));
+        B200_CUDA(cudaFree(idx->pending));
+      }
+      idx->pending = np;
+      idx->pending_cap = need;
+    }
+    dst = idx->pending + idx->npending * d;
+  } else {
+    B200_CHECK(idx->ntotal + n < (1ll << 32), B200_ERR_UNSUPPORTED, "add: a shard holds at most 2^32 rows");
+    B200_TRY(ensure_capacity(idx, idx->ntotal + n));
+    dst = idx->rows + idx->ntotal * d;
+  }
+  if (!f32) {
+    B200_CUDA(cudaMemcpy(dst, rows, (size_t)n * d * 2, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  } else {
+    const int64_t chunk = std::min<int64_t>(n, (64ll << 20) / d);  // rows per staging chunk
+    const float* src = (const float*)rows;
+    void* stage = nullptr;
+    if (!on_device) B200_TRY(index_ws(idx, 2, (size_t)chunk * d * 4, &stage));
+    for (int64_t r = 0; r < n; r += chunk) {
+      const int64_t m = std::min(chunk, n - r);
+      const float* dsrc = src + r * d;
+      if (!on_device) {
+        B200_CUDA(cudaMemcpy(stage, src + r * d, (size_t)m * d * 4, cudaMemcpyHostToDevice));
+        dsrc = (const float*)stage;
+      }
+      const int64_t count = m * d;
+      f32_to_f16_kernel<<<(unsigned)((count + 255) / 256), 256>>>(dsrc, dst + r * d, count);
+      B200_LAUNCH_OK();
+    }
+    B200_CUDA(cudaDeviceSynchronize());
+  }
+  if (idx->nlist > 0) idx->npending += n;
+  else idx->ntotal += n;
+  return B200_OK;
+}
+
+int b200_index_add_f16(b200_index* idx, const void* rows, int64_t n, int rows_on_device) {
+  return add_rows(idx, rows, n, rows_on_device, false);
+}
+int b200_index_add_f32(b200_index* idx, const float* rows, int64_t n, int rows_on_device) {
+  return add_rows(idx, rows, n, rows_on_device, true);
+}
+
+int b200_index_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec) {
+  B200_CHECK(idx && spec && n >= 0, B200_ERR_INVALID, "add_synthetic: bad argument");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(idx->device);
+  if (idx->nlist > 0) return ivf_add_synthetic(idx, n, row0, spec);
+  B200_CHECK(idx->ntotal + n < (1ll << 32), B200_ERR_UNSUPPORTED, "add: a shard holds at most 2^32 rows");
+  B200_TRY(ensure_capacity(idx, idx->ntotal + n));
+  B200_TRY(synth_rows<__half>(idx->rows + idx->ntotal * idx->d, n, idx->d, row0, spec, 0));
+  B200_CUDA(cudaDeviceSynchronize());
+  idx->ntotal += n;
+  return B200_OK;
+}
+
+int b200_index_finalize(b200_index* idx) {
+  B200_CHECK(idx, B200_ERR_INVALID, "finalize: null index");
+  if (idx->nlist == 0) return B200_OK;
+  DeviceGuard g(idx->device);
+  return ivf_finalize(idx);
+}
+
+int64_t b200_index_ntotal(const b200_index* idx) { return idx ? idx->ntotal + idx->npending : -1; }
+int b200_index_d(const b200_index* idx) { return idx ? idx->d : -1; }
+int b200_index_nlist(const b200_index* idx) { return idx ? idx->nlist : -1; }
+
+int b200_index_set_id_base(b200_index* idx, int64_t id_base) {
+  B200_CHECK(idx, B200_ERR_INVALID, "set_id_base: null index");
+  idx->id_base = id_base;
+  return B200_OK;
+}
+
+int b200_index_set_nprobe(b200_index* idx, int nprobe) {
+  B200_CHECK(idx, B200_ERR_INVALID, "set_nprobe: null index");
+  B200_CHECK(idx->nlist > 0, B200_ERR_STATE, "set_nprobe: not an IVF index");
+  B200_CHECK(nprobe >= 1, B200_ERR_INVALID, "set_nprobe: nprobe=%d", nprobe);
+  idx->nprobe = std::min(nprobe, idx->nlist);
+  return B200_OK;
+}
+int b200_index_get_nprobe(const b200_index* idx) { return idx ? idx->nprobe : -1; }
+
+int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids) {
+  B200_CHECK(idx && h_sizes, B200_ERR_INVALID, "ivf_lists: null argument");
+  B200_CHECK(idx->nlist > 0, B200_ERR_STATE, "ivf_lists: not an IVF index");
+  DeviceGuard g(idx->device);
+  B200_TRY(ivf_finalize(idx));
+  return ivf_lists(idx, h_sizes, h_ids);
+}
+
+int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k, float* d_D, int64_t* d_I, float* d_R,
+                             void* stream) {
+  B200_CHECK(idx, B200_ERR_INVALID, "search: null index");
+  DeviceGuard g(idx->device);
+  return search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, (cudaStream_t)stream);
+}
+
+int b200_index_search(b200_index* idx, const float* h_q, int nq, int k, float* h_D, int64_t* h_I, float* h_R) {
+  B200_CHECK(idx, B200_ERR_INVALID, "search: null index");
+  B200_CHECK(nq >= 0 && k >= 1, B200_ERR_INVALID, "search: bad nq=%d k=%d", nq, k);
+  if (nq == 0) return B200_OK;
+  B200_CHECK(h_q && h_D && h_I, B200_ERR_INVALID, "search: null buffer");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard g(idx->device);
+  const size_t qb = (size_t)nq * idx->d * 4, db = (size_t)nq * k * 4, ib = (size_t)nq * k * 8;
+  const size_t rb = h_R ? (size_t)nq * k * idx->d * 4 : 0;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  void* ws = nullptr;
+  B200_TRY(index_ws(idx, 2, al(qb) + al(db) + al(ib) + al(rb), &ws));
+  char* p = (char*)ws;
+  float* d_q = (float*)p; p += al(qb);
+  float* d_D = (float*)p; p += al(db);
+  int64_t* d_I = (int64_t*)p; p += al(ib);
+  float* d_R = h_R ? (float*)p : nullptr;
+  B200_CUDA(cudaMemcpyAsync(d_q, h_q, qb, cudaMemcpyHostToDevice, 0));
+  B200_TRY(search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, 0));
+  B200_CUDA(cudaMemcpyAsync(h_D, d_D, db, cudaMemcpyDeviceToHost, 0));
+  B200_CUDA(cudaMemcpyAsync(h_I, d_I, ib, cudaMemcpyDeviceToHost, 0));
+  if (h_R) B200_CUDA(cudaMemcpyAsync(h_R, d_R, rb, cudaMemcpyDeviceToHost, 0));
+  B200_CUDA(cudaStreamSynchronize(0));
+  return B200_OK;
+}
+
+int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t n, float* d_R, void* stream) {
+  B200_CHECK(idx && d_ids && d_R && n >= 0, B200_ERR_INVALID, "reconstruct: bad argument");
+  B200_CHECK(idx->nlist == 0, B200_ERR_UNSUPPORTED, "reconstruct by id is implemented for the flat index");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(idx->device);
+  gather_rows_from_slots_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      idx->rows, idx->d, d_ids, idx->id_base, idx->ntotal, nullptr, n, d_R);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+int b200_topk_merge_device(const float* d_Dg, const int64_t* d_Ig, int G, int nq, int k, float* d_D, int64_t* d_I,
+                           int device, void* stream) {
+  B200_CHECK(d_Dg && d_Ig && d_D && d_I && G >= 1 && nq >= 0 && k >= 1, B200_ERR_INVALID, "merge: bad argument");
+  if (nq == 0) return B200_OK;
+  int P = 2;
+  while (P < G * k) P <<= 1;
+  const size_t smem = (size_t)P * 4 + ((P & 1) ? 4 : 0) + (size_t)P * 8;
+  B200_CHECK(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "merge: G*k=%d exceeds 8192", G * k);
+  DeviceGuard g(device);
+  if (smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_shards_kernel<<<nq, 1024, smem, (cudaStream_t)stream>>>(d_Dg, d_Ig, G, nq, k, P, d_D, d_I);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+int b200_index_last_scan_ms(const b200_index* idx, float* ms, int* launches) {
+  B200_CHECK(idx && ms, B200_ERR_INVALID, "last_scan_ms: null argument");
+  DeviceGuard g(idx->device);
+  float total = 0.f;
+  for (int i = 0; i + 1 < idx->ev_used; i += 2) {
+    B200_CUDA(cudaEventSynchronize(idx->ev[i + 1]));
+    float t = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&t, idx->ev[i], idx->ev[i + 1]));
+    total += t;
+  }
+  *ms = total;
+  if (launches) *launches = idx->last_scan_launches;
+  return B200_OK;
+}
+
+}  // extern "C"

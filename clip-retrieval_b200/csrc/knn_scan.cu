@@ -1,0 +1,319 @@
+// Search path, exhaustive scan: the kernel behind index.search / search_and_reconstruct for the flat
+// index (reference call site clip_retrieval/clip_back.py:362) and behind the coarse step of IVF.
+//
+// HBM-bound design (nq small): every fp16 row is read exactly once with
+// 128-bit non-allocating loads, a warp owns U consecutive rows per step (U*d*2 bytes in flight per
+// warp), fp32 FMA against up to NQ queries held in registers, one transposing shuffle reduction
+// for the U*NQ dot products, and a per-warp replace-worst candidate list in shared memory that is
+// touched only when a score beats the list's current worst (k*(1+ln(n_warp/k)) times per warp).
+// Algorithmic bytes per launch: n * d * 2 (the row store); everything else is O(grid * k).
+#include "index.cuh"
+#include "topk.cuh"
+#include <float.h>
+#include <algorithm>
+
+namespace b200 {
+
+constexpr int SCAN_U = 4;
+
+template <int NQ, int CH>
+__global__ void __launch_bounds__(256)
+flat_scan_kernel(const uint4* __restrict__ X, int64_t n, int cpr, const float* __restrict__ Q, int nq_valid,
+                 int k, unsigned long long* __restrict__ out_keys, int64_t out_stride_q) {
+  extern __shared__ unsigned long long s_keys[];  // [warps][NQ][k]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned long long* wkeys = s_keys + (size_t)warp * NQ * k;
+  for (int i = lane; i < NQ * k; i += 32) wkeys[i] = 0ull;
+  __syncwarp();
+
+  // This lane's slice of each query: chunks lane, lane+32, ... (8 columns per chunk).
+  float qr[NQ][CH][8];
+  const int d = cpr * 8;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int ci = c * 32 + lane;
+      if (q < nq_valid && ci < cpr) {
+        const float4 a = *reinterpret_cast<const float4*>(Q + (size_t)q * d + ci * 8);
+        const float4 b = *reinterpret_cast<const float4*>(Q + (size_t)q * d + ci * 8 + 4);
+        qr[q][c][0] = a.x; qr[q][c][1] = a.y; qr[q][c][2] = a.z; qr[q][c][3] = a.w;
+        qr[q][c][4] = b.x; qr[q][c][5] = b.y; qr[q][c][6] = b.z; qr[q][c][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) qr[q][c][j] = 0.0f;
+      }
+    }
+  }
+
+  unsigned long long worst[NQ];
+  int worst_pos[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) { worst[q] = 0ull; worst_pos[q] = 0; }
+
+  constexpr int V = SCAN_U * NQ;
+  constexpr int SH = 5 - Log2<V>::v;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;
+  const int64_t total = (int64_t)gridDim.x * nwarps;
+  const int64_t nblk = (n + SCAN_U - 1) / SCAN_U;
+
+  for (int64_t blk = gw; blk < nblk; blk += total) {
+    const int64_t r0 = blk * SCAN_U;
+    uint4 v[SCAN_U][CH];
+#pragma unroll
+    for (int u = 0; u < SCAN_U; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int ci = c * 32 + lane;
+        if (r0 + u < n && ci < cpr) v[u][c] = ld_nc_v4(X + (r0 + u) * cpr + ci);
+        else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; i++) acc[i] = 0.0f;
+#pragma unroll
+    for (int u = 0; u < SCAN_U; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v[u][c]);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 t = __half22float2(h2[j]);
+          f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[u * NQ + q] = fmaf(f[j], qr[q][c][j], acc[u * NQ + q]);
+        }
+      }
+    }
+    warp_transpose_reduce<V>(acc, lane);
+    const float s = acc[0];
+    const int vi = lane >> SH;           // value index u*NQ+q held by this lane
+    const int my_q = vi % NQ;
+    const int64_t my_r = r0 + vi / NQ;
+    unsigned long long wq = worst[0];
+#pragma unroll
+    for (int q = 1; q < NQ; q++) if (my_q == q) wq = worst[q];
+    const unsigned long long key = make_key(s, (uint32_t)my_r);
+    const bool live = ((lane & ((1 << SH) - 1)) == 0) && my_r < n && my_q < nq_valid && (s == s);
+    unsigned pend = __ballot_sync(FULL, live && key > wq);
+    while (pend) {
+      const int src = __ffs(pend) - 1;
+      pend &= pend - 1;
+      const unsigned long long ckey = __shfl_sync(FULL, key, src);
+      const int cq = (src >> SH) % NQ;
+#pragma unroll
+      for (int q = 0; q < NQ; q++)
+        if (cq == q) warp_list_insert(wkeys + q * k, k, ckey, worst[q], worst_pos[q], lane);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    if (q < nq_valid) {
+      unsigned long long* o = out_keys + (int64_t)q * out_stride_q + gw * k;
+      for (int j = lane; j < k; j += 32) o[j] = wkeys[q * k + j];
+    }
+  }
+}
+
+// Select the k best of M candidate keys per query: grid (slices, nq); every block streams its
+// slice through a C-entry shared buffer, keeping a sorted top-k at the front.
+__global__ void __launch_bounds__(1024)
+topk_select_kernel(const unsigned long long* __restrict__ in, int64_t in_stride_q, int64_t M, int k, int C,
+                   unsigned long long* __restrict__ out, int64_t out_stride_q) {
+  extern __shared__ unsigned long long buf[];
+  const int q = blockIdx.y, s = blockIdx.x, slices = gridDim.x;
+  const int64_t per = (M + slices - 1) / slices;
+  const int64_t begin = (int64_t)s * per;
+  const int64_t end = begin + per < M ? begin + per : M;
+  const unsigned long long* src = in + (int64_t)q * in_stride_q;
+  int have = 0;
+  int64_t pos = begin;
+  do {
+    const int fill = C - have;
+    for (int i = threadIdx.x; i < fill; i += blockDim.x) {
+      const int64_t idx = pos + i;
+      buf[have + i] = idx < end ? src[idx] : 0ull;
+    }
+    pos += fill;
+    __syncthreads();
+    block_bitonic_sort_desc(buf, C);
+    have = k;
+  } while (pos < end);
+  unsigned long long* o = out + (int64_t)q * out_stride_q + (int64_t)s * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) o[j] = buf[j];
+}
+
+__global__ void decode_keys_kernel(const unsigned long long* __restrict__ keys, int64_t count, int64_t id_base,
+                                   const uint32_t* __restrict__ slot_to_id, float* __restrict__ D,
+                                   int64_t* __restrict__ I) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned long long key = keys[i];
+  if (key == 0ull) {
+    D[i] = -FLT_MAX;
+    I[i] = -1;
+  } else {
+    D[i] = key_score(key);
+    uint32_t id = key_id(key);
+    if (slot_to_id) id = slot_to_id[id];
+    I[i] = id_base + (int64_t)id;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+
+int index_ws(b200_index* idx, int slot, size_t bytes, void** out) {
+  if (idx->ws_bytes[slot] < bytes) {
+    if (idx->ws[slot]) B200_CUDA(cudaFree(idx->ws[slot]));
+    idx->ws[slot] = nullptr;
+    idx->ws_bytes[slot] = 0;
+    size_t want = bytes + (bytes >> 2);
+    B200_CUDA(cudaMalloc(&idx->ws[slot], want));
+    idx->ws_bytes[slot] = want;
+  }
+  *out = idx->ws[slot];
+  return B200_OK;
+}
+
+static int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+typedef void (*scan_fn)(const uint4*, int64_t, int, const float*, int, int, unsigned long long*, int64_t);
+
+template <int NQ>
+static scan_fn pick_ch(int ch) {
+  switch (ch) {
+    case 1: return flat_scan_kernel<NQ, 1>;
+    case 2: return flat_scan_kernel<NQ, 2>;
+    case 3: return flat_scan_kernel<NQ, 3>;
+  }
+  if constexpr (NQ <= 2) {
+    switch (ch) {
+      case 4: return flat_scan_kernel<NQ, 4>;
+      case 5: return flat_scan_kernel<NQ, 5>;
+      case 6: return flat_scan_kernel<NQ, 6>;
+    }
+  }
+  if constexpr (NQ == 1) {
+    switch (ch) {
+      case 7: return flat_scan_kernel<NQ, 7>;
+      case 8: return flat_scan_kernel<NQ, 8>;
+    }
+  }
+  return nullptr;
+}
+static scan_fn pick_scan(int nqp, int ch) {
+  if (nqp == 4) return pick_ch<4>(ch);
+  if (nqp == 2) return pick_ch<2>(ch);
+  return pick_ch<1>(ch);
+}
+
+struct ScanPlan {
+  int nqp;       // queries per pass
+  int threads;   // block size
+  int grid;
+  int C;         // select buffer entries
+  size_t smem;
+  scan_fn fn;
+};
+
+static int plan_scan(const b200_index* idx, int k, int nq, ScanPlan* p) {
+  const int ch = (idx->d / 8 + 31) / 32;
+  // queries per pass: the FMA path stays HBM-bound up to ~2 queries per pass; 4 trades some
+  // bandwidth for fewer passes when there are many queries.  nqp*ch bounds the query registers.
+  int nqp = nq >= 4 ? 4 : (nq >= 2 ? 2 : 1);
+  while (nqp > 1 && nqp * ch > 12) nqp >>= 1;
+  int threads = 256;
+  const size_t budget = 96 * 1024;  // keeps two blocks per SM
+  while (nqp > 1 && (size_t)(threads / 32) * nqp * k * 8 > budget) nqp >>= 1;
+  while (threads > 64 && (size_t)(threads / 32) * nqp * k * 8 > 200 * 1024) threads >>= 1;
+  p->C = std::max(2048, next_pow2(2 * k));
+  if ((size_t)(threads / 32) * nqp * k * 8 > 200 * 1024 || (size_t)p->C * 8 > 200 * 1024) {
+    set_error("search: k=%d exceeds the supported maximum (8192)", k);
+    return B200_ERR_UNSUPPORTED;
+  }
+  p->smem = (size_t)(threads / 32) * nqp * k * 8;
+  p->fn = pick_scan(nqp, ch);
+  if (!p->fn) {
+    set_error("search: unsupported dimension d=%d", idx->d);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (p->smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute((const void*)p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)p->fn, threads, p->smem));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  p->nqp = nqp;
+  p->threads = threads;
+  p->grid = idx->sms * per_sm;
+  return B200_OK;
+}
+
+int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* d_q, int nq, int k,
+                   unsigned long long* d_keys_out, cudaStream_t st) {
+  const int d = idx->d;
+  ScanPlan p;
+  B200_TRY(plan_scan(idx, k, nq, &p));
+  const int64_t total_warps = (int64_t)p.grid * (p.threads / 32);
+  const int64_t M1 = total_warps * k;
+  int slices = (int)std::min<int64_t>(64, std::max<int64_t>(1, M1 / (4 * (int64_t)(p.C - k))));
+  const int QB = 64;  // queries per batch (bounds the scratch)
+  const size_t keys1 = (size_t)QB * M1, keys2 = (size_t)QB * slices * k;
+  void* ws = nullptr;
+  B200_TRY(index_ws(idx, 0, (keys1 + keys2) * 8, &ws));
+  unsigned long long* k1 = (unsigned long long*)ws;
+  unsigned long long* k2 = k1 + keys1;
+  const size_t sel_smem = (size_t)p.C * 8;
+  if (sel_smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+
+  for (int q0 = 0; q0 < nq; q0 += QB) {
+    const int qb = std::min(QB, nq - q0);
+    // time the row-scan kernels of this batch
+    if ((int)idx->ev.size() < idx->ev_used + 2) {
+      cudaEvent_t a, b;
+      B200_CUDA(cudaEventCreate(&a));
+      B200_CUDA(cudaEventCreate(&b));
+      idx->ev.push_back(a);
+      idx->ev.push_back(b);
+    }
+    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
+    for (int qq = 0; qq < qb; qq += p.nqp) {
+      const int valid = std::min(p.nqp, qb - qq);
+      const float* qptr = d_q + (size_t)(q0 + qq) * d;
+      unsigned long long* kp = k1 + (size_t)qq * M1;
+      p.fn<<<p.grid, p.threads, p.smem, st>>>(reinterpret_cast<const uint4*>(rows), n, d / 8, qptr, valid, k, kp, M1);
+      B200_LAUNCH_OK();
+      idx->last_scan_launches++;
+    }
+    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
+    idx->ev_used += 2;
+    // level 1: slices per query; level 2: one block per query
+    topk_select_kernel<<<dim3(slices, qb), 1024, sel_smem, st>>>(k1, M1, M1, k, p.C, k2, (int64_t)slices * k);
+    B200_LAUNCH_OK();
+    topk_select_kernel<<<dim3(1, qb), 1024, sel_smem, st>>>(k2, (int64_t)slices * k, (int64_t)slices * k, k, p.C,
+                                                            d_keys_out + (size_t)q0 * k, k);
+    B200_LAUNCH_OK();
+  }
+  return B200_OK;
+}
+
+int decode_keys(const unsigned long long* keys, int64_t count, int64_t id_base, const uint32_t* slot_to_id, float* D,
+                int64_t* I, cudaStream_t st) {
+  if (count == 0) return B200_OK;
+  decode_keys_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(keys, count, id_base, slot_to_id, D, I);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+}  // namespace b200

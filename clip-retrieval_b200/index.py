@@ -1,0 +1,280 @@
+"""Index objects with the FAISS calling convention the reference uses.
+
+Reference seam: `ClipResource.image_index/text_index`
+(clip_retrieval/clip_back.py:781-782) are FAISS indices created by `load_index`
+(clip_back.py:589-596) and queried as
+    distances, indices, embeddings = index.search_and_reconstruct(query, num_result_ids)   # :362
+    D, I = index.search(x, k)                                                         # clip_filter.py:55
+with `query` a C-contiguous float32 [nq, d] array.  Results are numpy arrays owned by Python:
+D float32 [nq, k] descending, I int64 [nq, k] (-1 past the end), R float32 [nq, k, d].
+All arithmetic happens in the CUDA library (include/b200clip.h); nothing here computes.
+"""
+import ctypes as C
+import os
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+
+@dataclass
+class SynthSpec:
+    """Seeded synthetic rows (include/b200clip.h b200_synth_spec; oracle/synth_ref.py is the CPU twin)."""
+
+    seed: int = 1234
+    clustered: bool = False
+    centroid_seed: int = 7
+    nlist: int = 0
+    cw: int = 3
+    nw: int = 1
+
+    def c(self):
+        return _lib.SynthSpecC(self.seed, 1 if self.clustered else 0, self.centroid_seed, self.nlist, self.cw, self.nw)
+
+
+def _torch():
+    import torch  # device memory / streams only
+
+    return torch
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _as_query(x, d):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim != 2:
+        raise ValueError("query must be 2-D [nq, d], got shape %r" % (x.shape,))
+    assert x.shape[1] == d, "query dimension %d != index dimension %d" % (x.shape[1], d)  # FAISS asserts too
+    return x
+
+
+def synth_rows(n, d, spec, row0=0, dtype="float16", device=0):
+    """Rows row0..row0+n-1 of the synthetic set as a CUDA torch tensor (fp16 or fp32)."""
+    torch = _torch()
+    dt = torch.float16 if dtype in ("float16", "f16", torch.float16) else torch.float32
+    out = torch.empty((n, d), dtype=dt, device="cuda:%d" % device)
+    cs = spec.c()
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream().cuda_stream
+        fn = lib.b200_synth_rows_f16 if dt == torch.float16 else lib.b200_synth_rows_f32
+        check(fn(out.data_ptr(), n, d, row0, C.byref(cs), st), "synth_rows")
+    return out
+
+
+class _IndexBase:
+    def __init__(self):
+        self._h = C.c_void_p()
+        self._lock = threading.Lock()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.b200_index_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ---- FAISS attributes ----
+    @property
+    def ntotal(self):
+        return int(lib.b200_index_ntotal(self._h))
+
+    @property
+    def d(self):
+        return int(lib.b200_index_d(self._h))
+
+    @property
+    def is_trained(self):
+        return True
+
+    @property
+    def id_base(self):
+        return self._id_base
+
+    @id_base.setter
+    def id_base(self, v):
+        check(lib.b200_index_set_id_base(self._h, int(v)), "set_id_base")
+        self._id_base = int(v)
+
+    # ---- building ----
+    def reserve(self, n):
+        check(lib.b200_index_reserve(self._h, int(n)), "reserve")
+
+    def add(self, x):
+        """index.add(x): x is [n, d] float16/float32 numpy (host) or a CUDA torch tensor."""
+        if _is_torch(x):
+            torch = _torch()
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise ValueError("add: expected [n, %d], got %r" % (self.d, tuple(x.shape)))
+            x = x.contiguous()
+            on_dev = 1 if x.is_cuda else 0
+            if x.dtype == torch.float16:
+                check(lib.b200_index_add_f16(self._h, x.data_ptr(), x.shape[0], on_dev), "add")
+            elif x.dtype == torch.float32:
+                check(lib.b200_index_add_f32(self._h, x.data_ptr(), x.shape[0], on_dev), "add")
+            else:
+                raise TypeError("add: dtype %s not supported (float16/float32)" % x.dtype)
+            return
+        x = np.asarray(x)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError("add: expected [n, %d], got %r" % (self.d, x.shape))
+        if x.dtype == np.float16:
+            x = np.ascontiguousarray(x)
+            check(lib.b200_index_add_f16(self._h, x.ctypes.data, x.shape[0], 0), "add")
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            check(lib.b200_index_add_f32(self._h, x.ctypes.data, x.shape[0], 0), "add")
+
+    def add_synthetic(self, n, spec, row0=0):
+        cs = spec.c()
+        check(lib.b200_index_add_synthetic(self._h, int(n), int(row0), C.byref(cs)), "add_synthetic")
+
+    # ---- searching (host buffers: what the reference calls) ----
+    def search(self, x, k):
+        x = _as_query(x, self.d)
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        check(lib.b200_index_search(self._h, x.ctypes.data, nq, int(k), D.ctypes.data, I.ctypes.data, None), "search")
+        return D, I
+
+    def search_and_reconstruct(self, x, k):
+        x = _as_query(x, self.d)
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        R = np.empty((nq, k, self.d), dtype=np.float32)
+        check(
+            lib.b200_index_search(self._h, x.ctypes.data, nq, int(k), D.ctypes.data, I.ctypes.data, R.ctypes.data),
+            "search_and_reconstruct",
+        )
+        return D, I, R
+
+    # ---- searching (device buffers, asynchronous on the current stream) ----
+    def search_device(self, q, k, reconstruct=False):
+        """q: CUDA float32 torch tensor [nq, d].  Returns (D, I[, R]) CUDA tensors."""
+        torch = _torch()
+        if not (q.is_cuda and q.dtype == torch.float32 and q.dim() == 2 and q.shape[1] == self.d):
+            raise ValueError("search_device: q must be CUDA float32 [nq, %d]" % self.d)
+        q = q.contiguous()
+        nq = q.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        R = torch.empty((nq, k, self.d), dtype=torch.float32, device=q.device) if reconstruct else None
+        st = torch.cuda.current_stream(q.device).cuda_stream
+        with self._lock:
+            check(
+                lib.b200_index_search_device(
+                    self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), R.data_ptr() if reconstruct else None, st
+                ),
+                "search_device",
+            )
+        return (D, I, R) if reconstruct else (D, I)
+
+    def last_scan_ms(self):
+        ms = C.c_float(0)
+        n = C.c_int(0)
+        check(lib.b200_index_last_scan_ms(self._h, C.byref(ms), C.byref(n)), "last_scan_ms")
+        return float(ms.value), int(n.value)
+
+
+class B200FlatIndex(_IndexBase):
+    """Exhaustive inner-product index over fp16 rows (FAISS IndexFlatIP / "SQfp16" semantics)."""
+
+    def __init__(self, d, device=0):
+        super().__init__()
+        self._id_base = 0
+        self.device = device
+        check(lib.b200_index_create_flat(int(d), int(device), C.byref(self._h)), "create_flat")
+
+    def reconstruct(self, key):
+        torch = _torch()
+        ids = torch.tensor([int(key)], dtype=torch.int64, device="cuda:%d" % self.device)
+        out = torch.empty((1, self.d), dtype=torch.float32, device=ids.device)
+        st = torch.cuda.current_stream(ids.device).cuda_stream
+        check(lib.b200_index_reconstruct_device(self._h, ids.data_ptr(), 1, out.data_ptr(), st), "reconstruct")
+        return out[0].cpu().numpy()
+
+
+class B200IVFFlatIndex(_IndexBase):
+    """IVF-Flat, inner product, fp16 rows (FAISS "IVF{nlist},SQfp16" / IndexIVFFlat semantics).
+
+    `nprobe` is the knob the reference touches through faiss.extract_index_ivf(index).nprobe
+    (clip_back.py:357-361,368-369)."""
+
+    def __init__(self, d, nlist, centroids, device=0):
+        super().__init__()
+        self._id_base = 0
+        self.device = device
+        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        if c.shape != (nlist, d):
+            raise ValueError("centroids must be [%d, %d], got %r" % (nlist, d, c.shape))
+        check(lib.b200_index_create_ivfflat(int(d), int(nlist), c.ctypes.data, int(device), C.byref(self._h)), "create_ivfflat")
+
+    @property
+    def nlist(self):
+        return int(lib.b200_index_nlist(self._h))
+
+    @property
+    def nprobe(self):
+        return int(lib.b200_index_get_nprobe(self._h))
+
+    @nprobe.setter
+    def nprobe(self, v):
+        check(lib.b200_index_set_nprobe(self._h, int(v)), "set_nprobe")
+
+    def finalize(self):
+        check(lib.b200_index_finalize(self._h), "finalize")
+
+    def invlists(self):
+        """(sizes [nlist], ids concatenated list after list) — what
+        ivf_metadata_ordering.get_old_to_new_mapping reads from FAISS invlists (:46-64)."""
+        sizes = np.zeros(self.nlist, dtype=np.int64)
+        ids = np.zeros(self.ntotal, dtype=np.int64)
+        check(lib.b200_index_ivf_lists(self._h, sizes.ctypes.data, ids.ctypes.data), "ivf_lists")
+        return sizes, ids
+
+
+def load_index(path, enable_faiss_memory_mapping=False, device=0):
+    """Counterpart of clip_back.load_index (clip_back.py:589-596) for fp16 embedding shards.
+
+    `path` is a `.npy` file or a folder of `.npy` shards in the layout the reference writer
+    produces (`img_emb/img_emb_{i}.npy`, fp16 row-major; writer.py:67-87).  Shards are appended in
+    sorted file order, which is the global row id order.  The rows go
+    straight to HBM; `enable_faiss_memory_mapping` is accepted for signature parity and ignored.
+    """
+    del enable_faiss_memory_mapping
+    files = [path] if os.path.isfile(path) else sorted(
+        os.path.join(path, f) for f in os.listdir(path) if f.endswith(".npy")
+    )
+    if not files:
+        raise ValueError("load_index: no .npy shard under %s" % path)
+    first = np.load(files[0], mmap_mode="r")
+    index = B200FlatIndex(first.shape[1], device=device)
+    total = sum(np.load(f, mmap_mode="r").shape[0] for f in files)
+    index.reserve(total)
+    for f in files:
+        index.add(np.load(f))
+    return index
+
+
+def merge_shard_results(Dg, Ig, k):
+    """Merge per-shard candidates [G, nq, k] (CUDA tensors) into the global top-k [nq, k]."""
+    torch = _torch()
+    G, nq, kk = Dg.shape
+    assert kk == k and Ig.shape == Dg.shape
+    Dg = Dg.contiguous()
+    Ig = Ig.contiguous()
+    D = torch.empty((nq, k), dtype=torch.float32, device=Dg.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=Dg.device)
+    st = torch.cuda.current_stream(Dg.device).cuda_stream
+    check(
+        lib.b200_topk_merge_device(Dg.data_ptr(), Ig.data_ptr(), G, nq, k, D.data_ptr(), I.data_ptr(), Dg.device.index or 0, st),
+        "topk_merge",
+    )
+    return D, I

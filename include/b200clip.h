@@ -1,0 +1,189 @@
+/*
+ * b200clip.h — C ABI of the B200-native hot path for rom1504/clip-retrieval.
+ *
+ * The reference (pure Python) has no FFI of its own; its hot-path seams are duck-typed Python
+ * objects.  Each entry point below names the reference call it replaces.
+ * Conventions:
+ *   - every function returns 0 on success, a negative b200_status on failure; the message of the
+ *     last failure on the calling thread is b200_last_error().  No exception crosses this ABI.
+ *   - `h_` pointers are host memory, `d_` pointers are device memory on the handle's device.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device entry
+ *     points are asynchronous on `stream`; host entry points return after the result is in the
+ *     host buffers.
+ *   - the caller owns every buffer it passes in; the library owns what is behind the handles.
+ *   - a handle may be searched / encoded concurrently from several threads only through the host
+ *     entry points (they serialise on an internal mutex); `add`, `load`, `set_nprobe` are not
+ *     concurrent-safe with anything.
+ */
+#ifndef B200CLIP_H
+#define B200CLIP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,   /* bad argument */
+  B200_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  B200_ERR_OOM = -3,       /* device allocation failed */
+  B200_ERR_STATE = -4,     /* handle not in a state that allows the call */
+  B200_ERR_UNSUPPORTED = -5
+} b200_status;
+
+const char* b200_last_error(void);
+/* Library version string and the SM architecture it was compiled for ("sm_100a"). */
+const char* b200_version(void);
+/* Number of kernel launches this library has issued in this process (all handles, all streams).
+ * bench.py reads it before/after the timed region to report `gpu_launches`. */
+int64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic data (BASELINE.json configs are synthetic).  Counter-based and exactly reproducible
+ * on the CPU (oracle/synth_ref.py): integer noise, integer sum of squares, one fp64 sqrt/divide.
+ *   row r, col j:  noise(r,j) = sum of the 4 low bytes of splitmix64(seed, r, j) - 510
+ *   mode 0 (iid):        v = noise
+ *   mode 1 (clustered):  v = 8*noise(seed_c, list(r), j) + noise_scale_x8... see synth.cu
+ *   x = v / sqrt(sum v^2)  (fp64) -> fp32 -> fp16
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_synth_spec {
+  uint64_t seed;          /* noise seed */
+  int32_t  clustered;     /* 0: iid rows; 1: centroid[list(row)] * cw + noise * nw */
+  uint64_t centroid_seed; /* clustered: seed of the centroid rows */
+  int32_t  nlist;         /* clustered: number of centroids; list(row) = hash(row) % nlist */
+  int32_t  cw, nw;        /* clustered: integer weights of centroid and noise */
+} b200_synth_spec;
+
+/* Fill `d_out` ([n, d] row-major) with rows row0 .. row0+n-1 of the synthetic set. */
+int b200_synth_rows_f16(void* d_out, int64_t n, int d, int64_t row0, const b200_synth_spec* spec, void* stream);
+int b200_synth_rows_f32(float* d_out, int64_t n, int d, int64_t row0, const b200_synth_spec* spec, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Search path.  Replaces the FAISS index object held in ClipResource.image_index/text_index
+ * (reference clip_retrieval/clip_back.py:781-782), created by load_index (clip_back.py:589-596)
+ * and queried by KnnService.knn_search through index.search_and_reconstruct(query, k)
+ * (clip_back.py:362); secondary call sites index.search (clip_filter.py:55).
+ * Metric: inner product (cosine on normalised rows), fp16 storage, fp32 accumulation.
+ * Result order: score descending, ties by ascending id.  Unfilled slots: id -1, score -FLT_MAX,
+ * reconstructed row all-ones bits (NaN) — what FAISS returns and clip_back.py:370-378 truncates.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_index b200_index;
+
+/* Flat (exhaustive) index of dimension d (multiple of 8, <= 2048) on CUDA device `device`. */
+int b200_index_create_flat(int d, int device, b200_index** out);
+/* IVF-Flat: `h_centroids` is [nlist, d] fp32 on the host (rounded to fp16 inside, as the stored
+ * rows are).  Rows are assigned to the centroid of maximum inner product (FAISS IVF, IP metric). */
+int b200_index_create_ivfflat(int d, int nlist, const float* h_centroids, int device, b200_index** out);
+int b200_index_destroy(b200_index* idx);
+
+/* Pre-size the row store (rows); avoids regrowth copies for large shards. */
+int b200_index_reserve(b200_index* idx, int64_t n);
+/* Append n rows ([n, d] row-major).  Ids are insertion positions + id_base (see set_id_base). */
+int b200_index_add_f16(b200_index* idx, const void* rows, int64_t n, int rows_on_device);
+int b200_index_add_f32(b200_index* idx, const float* rows, int64_t n, int rows_on_device);
+/* Append n synthetic rows (rows row0.. of `spec`) generated directly in the row store. */
+int b200_index_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec);
+/* IVF only: rows appended since the last call are bucketed into their inverted lists.  Called
+ * implicitly by the first search after an add. */
+int b200_index_finalize(b200_index* idx);
+
+int64_t b200_index_ntotal(const b200_index* idx);
+int     b200_index_d(const b200_index* idx);
+int     b200_index_nlist(const b200_index* idx);               /* 0 for flat */
+/* Range sharding: returned ids are id_base + local insertion position. */
+int b200_index_set_id_base(b200_index* idx, int64_t id_base);
+/* IVF knob the reference touches through faiss.extract_index_ivf(index).nprobe
+ * (clip_back.py:357-361,368-369). */
+int b200_index_set_nprobe(b200_index* idx, int nprobe);
+int b200_index_get_nprobe(const b200_index* idx);
+/* IVF introspection used by ivf_metadata_ordering.get_old_to_new_mapping
+ * (ivf_metadata_ordering.py:46-64): sizes[nlist] and, list after list, the ids in list order. */
+int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
+
+/* index.search_and_reconstruct(x, k) / index.search(x, k) with HOST buffers (the call the
+ * reference makes): h_q fp32 [nq, d]; h_D fp32 [nq, k]; h_I int64 [nq, k]; h_R fp32 [nq, k, d] or
+ * NULL.  Copies in, searches, copies out, synchronises. */
+int b200_index_search(b200_index* idx, const float* h_q, int nq, int k,
+                      float* h_D, int64_t* h_I, float* h_R);
+/* Same with DEVICE buffers, asynchronous on `stream`. */
+int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k,
+                             float* d_D, int64_t* d_I, float* d_R, void* stream);
+/* reconstruct(id) for a batch of ids (device buffers): d_R [n, d] fp32; id -1 -> NaN row. */
+int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t n, float* d_R, void* stream);
+/* Merge G sorted candidate lists per query into one top-k (the step after the all-gather of
+ * per-shard candidates): d_Dg/d_Ig are [G, nq, k]; outputs [nq, k]. */
+int b200_topk_merge_device(const float* d_Dg, const int64_t* d_Ig, int G, int nq, int k,
+                           float* d_D, int64_t* d_I, int device, void* stream);
+/* Duration in milliseconds (CUDA events on the launching stream) of the row-scan kernels of the
+ * last search call on this handle, and how many such kernels it launched.  bench.py uses it for
+ * the roofline of the dominant kernel. */
+int b200_index_last_scan_ms(const b200_index* idx, float* ms, int* launches);
+
+/* ------------------------------------------------------------------------------------------
+ * Embed path.  Replaces the model object returned by all_clip.load_clip and used through
+ * model.encode_image / model.encode_text in ClipMapper.__call__
+ * (clip_retrieval/clip_inference/mapper.py:42-43,57-59,65-67) and KnnService.compute_query
+ * (clip_back.py:230-232,244-246), fused with the L2-normalise + cast that follows each call.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200_clip b200_clip;
+
+typedef struct b200_tower_config {
+  int32_t width, layers, heads, mlp;   /* transformer */
+} b200_tower_config;
+
+typedef struct b200_clip_config {
+  int32_t embed_dim;         /* D: output embedding dimension */
+  int32_t image_size, patch; /* 224, 14|32 */
+  b200_tower_config vision;
+  int32_t context_length;    /* 77 */
+  int32_t vocab_size;        /* 49408 */
+  b200_tower_config text;
+  int32_t quick_gelu;        /* 1: x*sigmoid(1.702x) (OpenAI weights); 0: exact erf GELU (LAION) */
+  int32_t max_batch;         /* activations are sized for this many samples per call */
+} b200_clip_config;
+
+typedef struct b200_tensor_view {
+  const char* name;    /* open_clip / OpenAI state_dict key, e.g. "visual.transformer.resblocks.0.attn.in_proj_weight" */
+  const void* data;    /* HOST pointer, contiguous */
+  int32_t dtype;       /* 0 = fp32, 1 = fp16 */
+  int32_t ndim;
+  int64_t shape[4];
+} b200_tensor_view;
+
+#define B200_OUT_F16 1
+#define B200_OUT_F32 0
+
+int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out);
+int b200_clip_destroy(b200_clip* m);
+/* Upload weights given as a state_dict in the open_clip/OpenAI key layout; converts to the
+ * packed bf16 device layout.  Missing or mis-shaped tensors are an error. */
+int b200_clip_load_weights(b200_clip* m, const b200_tensor_view* tensors, int n);
+/* encode_image + `/= norm` + cast: d_pixels fp32 NCHW [B,3,S,S]; d_out [B,D] fp16 or fp32.
+ * normalize=0 returns the raw projected features (what model.encode_image returns). */
+int b200_clip_encode_image_device(b200_clip* m, const float* d_pixels, int B, void* d_out,
+                                  int out_dtype, int normalize, void* stream);
+/* encode_text: d_tokens int64 [B, context_length]; pooled at argmax(tokens) (EOT). */
+int b200_clip_encode_text_device(b200_clip* m, const int64_t* d_tokens, int B, void* d_out,
+                                 int out_dtype, int normalize, void* stream);
+/* Host-buffer variants: the mapper call (H2D of the batch, forward, D2H of the embeddings). */
+int b200_clip_encode_image(b200_clip* m, const float* h_pixels, int B, void* h_out, int out_dtype, int normalize);
+int b200_clip_encode_text(b200_clip* m, const int64_t* h_tokens, int B, void* h_out, int out_dtype, int normalize);
+/* Per-kernel-class device time of the last encode call (ms, CUDA events): gemm, attention,
+ * layernorm, other; and number of kernel launches.  For bench.py's roofline. */
+int b200_clip_last_timing(const b200_clip* m, float* ms_by_class /*[4]*/, int* launches);
+/* Enable per-class event timing (adds event records between kernels; off by default). */
+int b200_clip_set_profiling(b200_clip* m, int on);
+
+/* Stand-alone GEMM entry used by the tests and the roofline bench of the tcgen05 core:
+ * C[M,N] (bf16) = act(A[M,K] (bf16, row-major) · W[N,K]^T (bf16, row-major) + bias[N] (fp32|NULL))
+ *               (+ residual[M,N] bf16 | NULL).  act: 0 none, 1 quick_gelu, 2 gelu(erf). */
+int b200_gemm_bf16_device(const void* d_A, const void* d_W, const float* d_bias, const void* d_residual,
+                          void* d_C, int M, int N, int K, int act, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H */
