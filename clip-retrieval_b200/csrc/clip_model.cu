@@ -1,14 +1,471 @@
-// Embed path handle (placeholder until the forward lands).
+// Embed path handle: the object behind model.encode_image / model.encode_text (reference
+// clip_retrieval/clip_inference/mapper.py:42-43,57-59,65-67 and clip_back.py:230-232,244-246),
+// fused with the L2-normalise + cast that follows each call in the reference.
+//
+// Data layout in HBM: weights packed once as bf16 [N, K] row-major (the layout both open_clip's
+// state_dict and the tcgen05 B operand use), LayerNorm affine / biases / positional tables fp32;
+// activations bf16 [B*T, width] row-major, one buffer per role (x residual stream, h LN output,
+// qkv, a attention output, f MLP hidden), sized for max_batch at create time so every TMA
+// descriptor is built once.
 #include "common.cuh"
-using namespace b200;
-extern "C" {
-int b200_clip_create(const b200_clip_config*, int, b200_clip**) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_destroy(b200_clip*) { return B200_OK; }
-int b200_clip_load_weights(b200_clip*, const b200_tensor_view*, int) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_encode_image_device(b200_clip*, const float*, int, void*, int, int, void*) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_encode_text_device(b200_clip*, const int64_t*, int, void*, int, int, void*) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_encode_image(b200_clip*, const float*, int, void*, int, int) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_encode_text(b200_clip*, const int64_t*, int, void*, int, int) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_last_timing(const b200_clip*, float*, int*) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
-int b200_clip_set_profiling(b200_clip*, int) { set_error("embed path not built yet"); return B200_ERR_UNSUPPORTED; }
+#include "embed_kernels.cuh"
+#include "gemm.cuh"
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cmath>
+
+namespace b200 {
+
+struct Linear {
+  __nv_bfloat16* w = nullptr;  // [N, K]
+  float* b = nullptr;          // [N] or null
+  int N = 0, K = 0;
+  CUtensorMap tm256, tm128;
+};
+
+struct Layer {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  Linear qkv, out, fc, proj;
+};
+
+struct Tower {
+  int width = 0, layers = 0, heads = 0, mlp = 0, T = 0;
+  std::vector<Layer> L;
+  // activations
+  __nv_bfloat16 *x = nullptr, *h = nullptr, *qkv = nullptr, *a = nullptr, *f = nullptr;
+  CUtensorMap tm_h, tm_a, tm_f;
+  float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
+  __nv_bfloat16* proj = nullptr;             // [width, D]
+};
+
+enum { CLS_GEMM = 0, CLS_ATTN = 1, CLS_LN = 2, CLS_OTHER = 3 };
+
+}  // namespace b200
+
+struct b200_clip {
+  b200_clip_config cfg;
+  int device = 0, sms = 148;
+  bool loaded = false;
+  b200::Tower vis, txt;
+  // vision front end
+  int grid = 0, Kp = 0;
+  b200::Linear conv;          // [w, Kp]
+  __nv_bfloat16* cols = nullptr;  // [max_batch*g*g, Kp]
+  CUtensorMap tm_cols;
+  __nv_bfloat16* vpos = nullptr;  // positional_embedding bf16 [T, w] (residual operand of the patch GEMM)
+  float* cls_pos0 = nullptr;      // class_embedding + positional_embedding[0]
+  float *lnpre_g = nullptr, *lnpre_b = nullptr;
+  // text front end
+  __nv_bfloat16* tok_emb = nullptr;  // [vocab, w]
+  float* tpos = nullptr;             // [ctx, w]
+  int* pool_idx = nullptr;
+  // staging for the host entry points
+  void* stage_in = nullptr;
+  void* stage_out = nullptr;
+  std::vector<void*> allocs;
+  std::mutex mu;
+  // timing
+  bool profiling = false;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  int span_used = 0;
+  int last_launches = 0;
+};
+
+namespace b200 {
+
+template <typename T>
+static int dev_alloc(b200_clip* m, T** p, size_t count) {
+  void* q = nullptr;
+  B200_CUDA(cudaMalloc(&q, count * sizeof(T)));
+  m->allocs.push_back(q);
+  *p = (T*)q;
+  return B200_OK;
 }
+
+static int make_linear(b200_clip* m, Linear* l, int N, int K, bool bias) {
+  l->N = N;
+  l->K = K;
+  B200_TRY(dev_alloc(m, &l->w, (size_t)N * K));
+  B200_CUDA(cudaMemset(l->w, 0, (size_t)N * K * 2));
+  if (bias) {
+    B200_TRY(dev_alloc(m, &l->b, (size_t)N));
+    B200_CUDA(cudaMemset(l->b, 0, (size_t)N * 4));
+  }
+  B200_TRY(make_tmap_2d(&l->tm256, l->w, 1, N, K, K, 256, GEMM_BK));
+  B200_TRY(make_tmap_2d(&l->tm128, l->w, 1, N, K, K, 128, GEMM_BK));
+  return B200_OK;
+}
+
+static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T, int D) {
+  t->width = c.width; t->layers = c.layers; t->heads = c.heads; t->mlp = c.mlp; t->T = T;
+  const int w = c.width;
+  const size_t rows = (size_t)m->cfg.max_batch * T;
+  B200_CHECK(w % 8 == 0 && c.mlp % 8 == 0 && w % c.heads == 0, B200_ERR_INVALID, "tower: width/mlp must be multiples of 8");
+  t->L.resize(c.layers);
+  for (auto& L : t->L) {
+    B200_TRY(dev_alloc(m, &L.ln1_g, (size_t)w)); B200_TRY(dev_alloc(m, &L.ln1_b, (size_t)w));
+    B200_TRY(dev_alloc(m, &L.ln2_g, (size_t)w)); B200_TRY(dev_alloc(m, &L.ln2_b, (size_t)w));
+    B200_TRY(make_linear(m, &L.qkv, 3 * w, w, true));
+    B200_TRY(make_linear(m, &L.out, w, w, true));
+    B200_TRY(make_linear(m, &L.fc, c.mlp, w, true));
+    B200_TRY(make_linear(m, &L.proj, w, c.mlp, true));
+  }
+  B200_TRY(dev_alloc(m, &t->lnf_g, (size_t)w)); B200_TRY(dev_alloc(m, &t->lnf_b, (size_t)w));
+  B200_TRY(dev_alloc(m, &t->proj, (size_t)w * D));
+  B200_TRY(dev_alloc(m, &t->x, rows * w));
+  B200_TRY(dev_alloc(m, &t->h, rows * w));
+  B200_TRY(dev_alloc(m, &t->qkv, rows * 3 * w));
+  B200_TRY(dev_alloc(m, &t->a, rows * w));
+  B200_TRY(dev_alloc(m, &t->f, rows * c.mlp));
+  B200_TRY(make_tmap_2d(&t->tm_h, t->h, 1, rows, w, w, GEMM_BM, GEMM_BK));
+  B200_TRY(make_tmap_2d(&t->tm_a, t->a, 1, rows, w, w, GEMM_BM, GEMM_BK));
+  B200_TRY(make_tmap_2d(&t->tm_f, t->f, 1, rows, c.mlp, c.mlp, GEMM_BM, GEMM_BK));
+  return B200_OK;
+}
+
+// ---- timing spans ------------------------------------------------------------------------------
+struct SpanGuard {
+  b200_clip* m; cudaStream_t st; int idx = -1;
+  SpanGuard(b200_clip* m_, int cls, cudaStream_t s) : m(m_), st(s) {
+    if (!m->profiling) return;
+    if (m->span_used == (int)m->spans.size()) {
+      b200_clip::Span sp;
+      sp.cls = cls;
+      if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+      m->spans.push_back(sp);
+    }
+    idx = m->span_used++;
+    m->spans[idx].cls = cls;
+    cudaEventRecord(m->spans[idx].a, st);
+  }
+  ~SpanGuard() {
+    if (idx >= 0) cudaEventRecord(m->spans[idx].b, st);
+  }
+};
+
+static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int M, GemmEpilogue ep, cudaStream_t st) {
+  SpanGuard sg(m, CLS_GEMM, st);
+  const int bn = gemm_pick_bn(M, l.N, m->sms);
+  ep.bias = l.b;
+  m->last_launches++;
+  return gemm_bf16_launch(tmA, bn == 256 ? l.tm256 : l.tm128, bn, M, l.N, l.K, ep, m->sms, st);
+}
+
+static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st) {
+  const int w = t.width;
+  const int M = B * t.T;
+  const int act = m->cfg.quick_gelu ? ACT_QUICK_GELU : ACT_GELU;
+  for (auto& L : t.L) {
+    { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+      B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln1_g, L.ln1_b, M, w, st)); }
+    GemmEpilogue e1; e1.out = t.qkv; e1.out_ld = 3 * w;
+    B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st));
+    { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
+      B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
+    GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
+    B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st));
+    { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+      B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln2_g, L.ln2_b, M, w, st)); }
+    GemmEpilogue e3; e3.out = t.f; e3.out_ld = t.mlp; e3.act = act;
+    B200_TRY(run_linear(m, t.tm_h, L.fc, M, e3, st));
+    GemmEpilogue e4; e4.out = t.x; e4.out_ld = w; e4.residual = t.x; e4.res_ld = w;
+    B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st));
+  }
+  return B200_OK;
+}
+
+static int encode_image_chunk(b200_clip* m, const float* d_px, int B, void* d_out, int out_f16, int normalize,
+                              cudaStream_t st) {
+  Tower& t = m->vis;
+  const int g = m->grid, w = t.width, T = t.T;
+  { SpanGuard sg(m, CLS_OTHER, st); m->last_launches += 2;
+    B200_TRY(im2col_patches(d_px, m->cols, B, m->cfg.image_size, m->cfg.patch, m->Kp, st));
+    B200_TRY(write_cls_rows(t.x, m->cls_pos0, B, T, w, st)); }
+  // patch embedding: x[b*T + 1 + p, :] = cols[b*g*g + p, :] · conv^T + positional_embedding[1 + p]
+  GemmEpilogue ep; ep.out = t.x; ep.out_ld = w; ep.out_group = g * g;
+  ep.residual = m->vpos; ep.res_ld = w; ep.res_row_mod = g * g; ep.res_row_off = 1;
+  B200_TRY(run_linear(m, m->tm_cols, m->conv, B * g * g, ep, st));
+  { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+    B200_TRY(layernorm_rows(t.x, w, t.x, w, m->lnpre_g, m->lnpre_b, (int64_t)B * T, w, st)); }
+  B200_TRY(run_blocks(m, t, B, 0, st));
+  { SpanGuard sg(m, CLS_OTHER, st); m->last_launches++;
+    B200_TRY(pool_ln_proj_norm(t.x, T, w, nullptr, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st)); }
+  return B200_OK;
+}
+
+static int encode_text_chunk(b200_clip* m, const int64_t* d_tok, int B, void* d_out, int out_f16, int normalize,
+                             cudaStream_t st) {
+  Tower& t = m->txt;
+  const int w = t.width, T = t.T;
+  { SpanGuard sg(m, CLS_OTHER, st); m->last_launches += 2;
+    B200_TRY(text_embed(d_tok, m->tok_emb, m->tpos, t.x, B, T, w, m->cfg.vocab_size, st));
+    B200_TRY(token_argmax(d_tok, m->pool_idx, B, T, st)); }
+  B200_TRY(run_blocks(m, t, B, 1, st));
+  { SpanGuard sg(m, CLS_OTHER, st); m->last_launches++;
+    B200_TRY(pool_ln_proj_norm(t.x, T, w, m->pool_idx, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st)); }
+  return B200_OK;
+}
+
+// ---- weight upload -------------------------------------------------------------------------------
+static inline float view_get(const b200_tensor_view& v, size_t i) {
+  if (v.dtype == 0) return ((const float*)v.data)[i];
+  return __half2float(((const __half*)v.data)[i]);
+}
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static size_t view_count(const b200_tensor_view& v) {
+  size_t n = 1;
+  for (int i = 0; i < v.ndim; i++) n *= (size_t)v.shape[i];
+  return n;
+}
+
+struct Loader {
+  std::map<std::string, const b200_tensor_view*> by_name;
+  std::vector<uint16_t> tmp16;
+  std::vector<float> tmp32;
+  const b200_tensor_view* find(const std::string& name, size_t count) {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) { set_error("load_weights: tensor '%s' is missing", name.c_str()); return nullptr; }
+    if (view_count(*it->second) != count) {
+      set_error("load_weights: tensor '%s' has %zu elements, expected %zu", name.c_str(), view_count(*it->second), count);
+      return nullptr;
+    }
+    return it->second;
+  }
+  // dst bf16 [rows, dst_ld] <- src [rows, cols] (zero padded columns keep their zeros)
+  int put_bf16(const std::string& name, __nv_bfloat16* dst, size_t rows, size_t cols, size_t dst_ld) {
+    const b200_tensor_view* v = find(name, rows * cols);
+    if (!v) return B200_ERR_INVALID;
+    tmp16.assign(rows * dst_ld, 0);
+    for (size_t r = 0; r < rows; r++)
+      for (size_t c = 0; c < cols; c++) tmp16[r * dst_ld + c] = f32_to_bf16_rn(view_get(*v, r * cols + c));
+    B200_CUDA(cudaMemcpy(dst, tmp16.data(), tmp16.size() * 2, cudaMemcpyHostToDevice));
+    return B200_OK;
+  }
+  int put_f32(const std::string& name, float* dst, size_t count) {
+    const b200_tensor_view* v = find(name, count);
+    if (!v) return B200_ERR_INVALID;
+    tmp32.resize(count);
+    for (size_t i = 0; i < count; i++) tmp32[i] = view_get(*v, i);
+    B200_CUDA(cudaMemcpy(dst, tmp32.data(), count * 4, cudaMemcpyHostToDevice));
+    return B200_OK;
+  }
+};
+
+static int load_tower(Loader& ld, Tower& t, const std::string& prefix) {
+  const size_t w = t.width, mlp = t.mlp;
+  for (int i = 0; i < t.layers; i++) {
+    Layer& L = t.L[i];
+    const std::string p = prefix + "transformer.resblocks." + std::to_string(i) + ".";
+    B200_TRY(ld.put_f32(p + "ln_1.weight", L.ln1_g, w));
+    B200_TRY(ld.put_f32(p + "ln_1.bias", L.ln1_b, w));
+    B200_TRY(ld.put_bf16(p + "attn.in_proj_weight", L.qkv.w, 3 * w, w, w));
+    B200_TRY(ld.put_f32(p + "attn.in_proj_bias", L.qkv.b, 3 * w));
+    B200_TRY(ld.put_bf16(p + "attn.out_proj.weight", L.out.w, w, w, w));
+    B200_TRY(ld.put_f32(p + "attn.out_proj.bias", L.out.b, w));
+    B200_TRY(ld.put_f32(p + "ln_2.weight", L.ln2_g, w));
+    B200_TRY(ld.put_f32(p + "ln_2.bias", L.ln2_b, w));
+    B200_TRY(ld.put_bf16(p + "mlp.c_fc.weight", L.fc.w, mlp, w, w));
+    B200_TRY(ld.put_f32(p + "mlp.c_fc.bias", L.fc.b, mlp));
+    B200_TRY(ld.put_bf16(p + "mlp.c_proj.weight", L.proj.w, w, mlp, mlp));
+    B200_TRY(ld.put_f32(p + "mlp.c_proj.bias", L.proj.b, w));
+  }
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
+  B200_CHECK(cfg && out, B200_ERR_INVALID, "clip_create: null argument");
+  B200_CHECK(cfg->max_batch >= 1 && cfg->embed_dim >= 8 && cfg->patch >= 1 && cfg->image_size >= cfg->patch &&
+                 cfg->context_length >= 1 && cfg->vocab_size >= 2,
+             B200_ERR_INVALID, "clip_create: bad config");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  B200_CHECK(device >= 0 && device < ndev, B200_ERR_INVALID, "clip_create: device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  b200_clip* m = new (std::nothrow) b200_clip();
+  B200_CHECK(m != nullptr, B200_ERR_OOM, "clip_create: host allocation failed");
+  m->cfg = *cfg;
+  m->device = device;
+  m->sms = sm_count(device);
+  m->grid = cfg->image_size / cfg->patch;
+  const int k_raw = 3 * cfg->patch * cfg->patch;
+  m->Kp = (k_raw + 63) / 64 * 64;
+  const int T = m->grid * m->grid + 1;
+  int rc = B200_OK;
+  auto build = [&]() -> int {
+    B200_TRY(make_tower(m, &m->vis, cfg->vision, T, cfg->embed_dim));
+    B200_TRY(make_tower(m, &m->txt, cfg->text, cfg->context_length, cfg->embed_dim));
+    B200_TRY(make_linear(m, &m->conv, cfg->vision.width, m->Kp, false));
+    const size_t prow = (size_t)cfg->max_batch * m->grid * m->grid;
+    B200_TRY(dev_alloc(m, &m->cols, prow * m->Kp));
+    B200_CUDA(cudaMemset(m->cols, 0, prow * m->Kp * 2));
+    B200_TRY(make_tmap_2d(&m->tm_cols, m->cols, 1, prow, m->Kp, m->Kp, GEMM_BM, GEMM_BK));
+    B200_TRY(dev_alloc(m, &m->vpos, (size_t)T * cfg->vision.width));
+    B200_TRY(dev_alloc(m, &m->cls_pos0, (size_t)cfg->vision.width));
+    B200_TRY(dev_alloc(m, &m->lnpre_g, (size_t)cfg->vision.width));
+    B200_TRY(dev_alloc(m, &m->lnpre_b, (size_t)cfg->vision.width));
+    B200_TRY(dev_alloc(m, &m->tok_emb, (size_t)cfg->vocab_size * cfg->text.width));
+    B200_TRY(dev_alloc(m, &m->tpos, (size_t)cfg->context_length * cfg->text.width));
+    B200_TRY(dev_alloc(m, &m->pool_idx, (size_t)cfg->max_batch));
+    const size_t in_bytes = std::max((size_t)cfg->max_batch * 3 * cfg->image_size * cfg->image_size * 4,
+                                     (size_t)cfg->max_batch * cfg->context_length * 8);
+    B200_CUDA(cudaMalloc(&m->stage_in, in_bytes));
+    m->allocs.push_back(m->stage_in);
+    B200_CUDA(cudaMalloc(&m->stage_out, (size_t)cfg->max_batch * cfg->embed_dim * 4));
+    m->allocs.push_back(m->stage_out);
+    return B200_OK;
+  };
+  rc = build();
+  if (rc != B200_OK) {
+    b200_clip_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return B200_OK;
+}
+
+int b200_clip_destroy(b200_clip* m) {
+  if (!m) return B200_OK;
+  DeviceGuard g(m->device);
+  cudaDeviceSynchronize();
+  for (void* p : m->allocs) cudaFree(p);
+  for (auto& s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  delete m;
+  return B200_OK;
+}
+
+int b200_clip_load_weights(b200_clip* m, const b200_tensor_view* tensors, int n) {
+  B200_CHECK(m && tensors && n > 0, B200_ERR_INVALID, "load_weights: bad argument");
+  DeviceGuard g(m->device);
+  Loader ld;
+  for (int i = 0; i < n; i++) {
+    B200_CHECK(tensors[i].name && tensors[i].data && (tensors[i].dtype == 0 || tensors[i].dtype == 1) &&
+                   tensors[i].ndim >= 0 && tensors[i].ndim <= 4,
+               B200_ERR_INVALID, "load_weights: malformed tensor view %d", i);
+    ld.by_name[tensors[i].name] = &tensors[i];
+  }
+  const b200_clip_config& c = m->cfg;
+  const size_t vw = c.vision.width, tw = c.text.width, D = c.embed_dim;
+  const size_t T = (size_t)m->grid * m->grid + 1, kraw = (size_t)3 * c.patch * c.patch;
+  B200_TRY(ld.put_bf16("visual.conv1.weight", m->conv.w, vw, kraw, m->Kp));
+  B200_TRY(ld.put_bf16("visual.positional_embedding", m->vpos, T, vw, vw));
+  {
+    const b200_tensor_view* cls = ld.find("visual.class_embedding", vw);
+    const b200_tensor_view* pos = ld.find("visual.positional_embedding", T * vw);
+    if (!cls || !pos) return B200_ERR_INVALID;
+    std::vector<float> v(vw);
+    for (size_t j = 0; j < vw; j++) v[j] = view_get(*cls, j) + view_get(*pos, j);
+    B200_CUDA(cudaMemcpy(m->cls_pos0, v.data(), vw * 4, cudaMemcpyHostToDevice));
+  }
+  B200_TRY(ld.put_f32("visual.ln_pre.weight", m->lnpre_g, vw));
+  B200_TRY(ld.put_f32("visual.ln_pre.bias", m->lnpre_b, vw));
+  B200_TRY(load_tower(ld, m->vis, "visual."));
+  B200_TRY(ld.put_f32("visual.ln_post.weight", m->vis.lnf_g, vw));
+  B200_TRY(ld.put_f32("visual.ln_post.bias", m->vis.lnf_b, vw));
+  B200_TRY(ld.put_bf16("visual.proj", m->vis.proj, vw, D, D));
+  B200_TRY(ld.put_bf16("token_embedding.weight", m->tok_emb, (size_t)c.vocab_size, tw, tw));
+  B200_TRY(ld.put_f32("positional_embedding", m->tpos, (size_t)c.context_length * tw));
+  B200_TRY(load_tower(ld, m->txt, ""));
+  B200_TRY(ld.put_f32("ln_final.weight", m->txt.lnf_g, tw));
+  B200_TRY(ld.put_f32("ln_final.bias", m->txt.lnf_b, tw));
+  B200_TRY(ld.put_bf16("text_projection", m->txt.proj, tw, D, D));
+  B200_CUDA(cudaDeviceSynchronize());
+  m->loaded = true;
+  return B200_OK;
+}
+
+static int encode_device(b200_clip* m, const void* d_in, int B, void* d_out, int out_dtype, int normalize, bool image,
+                         cudaStream_t st) {
+  B200_CHECK(m && (B == 0 || (d_in && d_out)) && B >= 0, B200_ERR_INVALID, "encode: bad argument");
+  B200_CHECK(m->loaded, B200_ERR_STATE, "encode: weights not loaded");
+  B200_CHECK(out_dtype == B200_OUT_F16 || out_dtype == B200_OUT_F32, B200_ERR_INVALID, "encode: out_dtype %d", out_dtype);
+  DeviceGuard g(m->device);
+  m->span_used = 0;
+  m->last_launches = 0;
+  const int mb = m->cfg.max_batch;
+  const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
+  const size_t out_stride = (size_t)m->cfg.embed_dim * (out_dtype == B200_OUT_F16 ? 2 : 4);
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    const char* in = (const char*)d_in + (size_t)b0 * in_stride;
+    char* o = (char*)d_out + (size_t)b0 * out_stride;
+    if (image) B200_TRY(encode_image_chunk(m, (const float*)in, nb, o, out_dtype == B200_OUT_F16, normalize, st));
+    else B200_TRY(encode_text_chunk(m, (const int64_t*)in, nb, o, out_dtype == B200_OUT_F16, normalize, st));
+  }
+  return B200_OK;
+}
+
+int b200_clip_encode_image_device(b200_clip* m, const float* d_pixels, int B, void* d_out, int out_dtype, int normalize,
+                                  void* stream) {
+  return encode_device(m, d_pixels, B, d_out, out_dtype, normalize, true, (cudaStream_t)stream);
+}
+int b200_clip_encode_text_device(b200_clip* m, const int64_t* d_tokens, int B, void* d_out, int out_dtype, int normalize,
+                                 void* stream) {
+  return encode_device(m, d_tokens, B, d_out, out_dtype, normalize, false, (cudaStream_t)stream);
+}
+
+static int encode_host(b200_clip* m, const void* h_in, int B, void* h_out, int out_dtype, int normalize, bool image) {
+  B200_CHECK(m && (B == 0 || (h_in && h_out)) && B >= 0, B200_ERR_INVALID, "encode: bad argument");
+  B200_CHECK(m->loaded, B200_ERR_STATE, "encode: weights not loaded");
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard g(m->device);
+  const int mb = m->cfg.max_batch;
+  const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
+  const size_t out_stride = (size_t)m->cfg.embed_dim * (out_dtype == B200_OUT_F16 ? 2 : 4);
+  int launches = 0;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    B200_CUDA(cudaMemcpyAsync(m->stage_in, (const char*)h_in + (size_t)b0 * in_stride, nb * in_stride, cudaMemcpyHostToDevice, 0));
+    B200_TRY(encode_device(m, m->stage_in, nb, m->stage_out, out_dtype, normalize, image, 0));
+    launches += m->last_launches;
+    B200_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, m->stage_out, nb * out_stride, cudaMemcpyDeviceToHost, 0));
+  }
+  B200_CUDA(cudaStreamSynchronize(0));
+  m->last_launches = launches;
+  return B200_OK;
+}
+
+int b200_clip_encode_image(b200_clip* m, const float* h_pixels, int B, void* h_out, int out_dtype, int normalize) {
+  return encode_host(m, h_pixels, B, h_out, out_dtype, normalize, true);
+}
+int b200_clip_encode_text(b200_clip* m, const int64_t* h_tokens, int B, void* h_out, int out_dtype, int normalize) {
+  return encode_host(m, h_tokens, B, h_out, out_dtype, normalize, false);
+}
+
+int b200_clip_set_profiling(b200_clip* m, int on) {
+  B200_CHECK(m, B200_ERR_INVALID, "set_profiling: null handle");
+  m->profiling = on != 0;
+  return B200_OK;
+}
+
+int b200_clip_last_timing(const b200_clip* m, float* ms_by_class, int* launches) {
+  B200_CHECK(m && ms_by_class, B200_ERR_INVALID, "last_timing: null argument");
+  DeviceGuard g(m->device);
+  for (int i = 0; i < 4; i++) ms_by_class[i] = 0.f;
+  for (int i = 0; i < m->span_used; i++) {
+    const auto& s = m->spans[i];
+    B200_CUDA(cudaEventSynchronize(s.b));
+    float t = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
+    if (s.cls >= 0 && s.cls < 4) ms_by_class[s.cls] += t;
+  }
+  if (launches) *launches = m->last_launches;
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+"""tcgen05 GEMM core vs a plain fp32 PyTorch reference of the same op (floating-point kernel:
+tolerance = bf16 output rounding 2^-8 relative + accumulation noise, stated per assert)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, W, b, R, act):
+    import torch
+
+    ref = A.float() @ W.float().t()
+    if b is not None:
+        ref = ref + b
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    if R is not None:
+        ref = ref + R.float()
+    return ref
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize(
+    "M,N,K,act,bias,res",
+    [
+        (128, 256, 64, 0, False, False),
+        (1, 512, 512, 0, True, False),        # single row (B=1 serving shape)
+        (257, 768, 768, 1, True, True),       # ragged M
+        (77 * 3, 2304, 768, 0, True, False),  # text QKV
+        (1000, 3072, 1024, 2, True, True),
+        (300, 1280, 1280, 0, True, True),     # H/14 width: 128-wide column blocks
+        (130, 520, 328, 1, True, True),       # N, K not multiples of the tile: TMA zero fill + predication
+        (4112, 4096, 1024, 1, True, False),
+        (4112, 1024, 4096, 0, True, True),
+    ],
+)
+def test_gemm_matches_fp32_reference(M, N, K, act, bias, res):
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    g = torch.Generator(device="cuda").manual_seed(M + 31 * N + 977 * K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    R = torch.randn(M, N, device="cuda", generator=g).bfloat16() if res else None
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.b200_gemm_bf16_device(A.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None,
+                                    R.data_ptr() if res else None, out.data_ptr(), M, N, K, act, 0, st), "gemm")
+    torch.cuda.synchronize()
+    ref = _ref(A, W, b, R, act)
+    err = (out.float() - ref).abs()
+    # bf16 output: half an ulp = 2^-9 relative; allow 2^-7 relative + 0.02 absolute for the fp32 sums
+    assert not torch.isnan(out.float()).any()
+    assert bool((err <= ref.abs() * 2 ** -7 + 0.02).all()), "max err %g" % err.max().item()
