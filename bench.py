@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (contract: see DESIGN.md §Measurement).
+
+Default workload = BASELINE.json configs[1]: ViT-L/14 image+text inference, synthetic 224^2,
+batch 1024 per GPU.  One step = one batch of 1024 images + 1024 captions through the embed path
+(encode_image + encode_text, L2-normalise, fp16).  Prints ONE JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--workload vitl14|knn] [--batch B] [--knn-rows N] [--no-knn]
+
+`value`  : pairs/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : pairs/s through the ClipMapper drop-in with pinned HOST tensors (H2D + D2H inside).
+`roofline`: tcgen05 GEMM kernel, algorithmic 2*M*N*K flops / event-timed GEMM time, against the
+            measured sustained bf16 peak of MEASURED_PEAKS.json.
+`knn`    : secondary object — brute-force kNN (BASELINE.json configs[2]) QPS + HBM roofline.
+`--impl reference`: the CPU oracle port of the same workload on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ---- algorithmic work -----------------------------------------
+def tower_gemm_flops(t, tokens):
+    w, mlp = t.width, t.mlp
+    per_layer = 2 * tokens * (w * 3 * w + w * w + w * mlp + mlp * w)
+    return t.layers * per_layer
+
+
+def tower_attn_flops(t, T):
+    return t.layers * 4 * T * T * t.width
+
+
+def arch_flops(arch):
+    g = arch.image_size // arch.patch
+    Ti, Tt = g * g + 1, arch.context_length
+    img_gemm = tower_gemm_flops(arch.vision, Ti) + 2 * (g * g) * arch.vision.width * 3 * arch.patch ** 2
+    txt_gemm = tower_gemm_flops(arch.text, Tt)
+    img = img_gemm + tower_attn_flops(arch.vision, Ti) + 2 * arch.vision.width * arch.embed_dim
+    txt = txt_gemm + tower_attn_flops(arch.text, Tt) + 2 * arch.text.width * arch.embed_dim
+    return {"image": img, "text": txt, "pair": img + txt, "image_gemm": img_gemm, "text_gemm": txt_gemm}
+
+
+# ---- clocks sampling ----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(s for s, p in zip(sm, power) if p > 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ---- CPU baseline (oracle port) -------------------------------------------------------------------------
+def cpu_baseline_embed(arch_name, n_sample):
+    import torch
+    from oracle import clip_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = clip_ref.CONFIGS[arch_name]
+    sd = clip_ref.make_state_dict(cfg, seed=0)
+    px = clip_ref.synth_images(n_sample, cfg, seed=3)
+    tk = clip_ref.synth_tokens(n_sample, cfg, seed=3)
+    clip_ref.mapper_image(sd, cfg, px[:1]); clip_ref.mapper_text(sd, cfg, tk[:1])  # warm-up
+    t0 = time.perf_counter()
+    clip_ref.mapper_image(sd, cfg, px)
+    clip_ref.mapper_text(sd, cfg, tk)
+    dt = time.perf_counter() - t0
+    return {"value": n_sample / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "%d image+text pairs of %s, fp32 oracle/clip_ref.py, torch %d threads, %.1f s" % (n_sample, arch_name, cores, dt)}
+
+
+def cpu_baseline_knn(n_rows, d, nq, k):
+    import numpy as np
+    import torch
+    from oracle import knn_ref, synth_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    X = synth_ref.rows_f16(n_rows, d, seed=1234)
+    Q = synth_ref.rows_f32(nq, d, seed=4321)
+    t0 = time.perf_counter()
+    knn_ref.flat_search(X, Q, k)
+    dt = time.perf_counter() - t0
+    return {"rows": n_rows, "nq": nq, "seconds": dt, "cores": cores}
+
+
+# ---- the B200 arm ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import clip_retrieval_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    arch_name = "ViT-L/14"
+    arch = m.ARCHS[arch_name]
+    fl = arch_flops(arch)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    if args.workload == "vitl14":
+        model = m.B200Clip(arch, device=local, max_batch=B)
+        model.load_state_dict(m.synthetic_state_dict(arch, seed=0))
+        g = torch.Generator().manual_seed(1000 + rank)
+        px_host = torch.randn(B, 3, arch.image_size, arch.image_size, generator=g).clamp_(-1.80, 2.15).pin_memory()
+        tok_host = torch.zeros(B, arch.context_length, dtype=torch.int64)
+        lens = torch.randint(3, arch.context_length - 2, (B,), generator=g)
+        for i in range(B):
+            L = int(lens[i])
+            tok_host[i, 0] = arch.vocab_size - 2
+            tok_host[i, 1:1 + L] = torch.randint(1, arch.vocab_size - 2, (L,), generator=g)
+            tok_host[i, 1 + L] = arch.vocab_size - 1
+        tok_host = tok_host.pin_memory()
+        px_dev, tok_dev = px_host.to(dev), tok_host.to(dev)
+
+        def step_device():
+            model.embed_image_device(px_dev)
+            model.embed_text_device(tok_dev)
+
+        for _ in range(W):
+            step_device()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        model.set_profiling(True)
+        gemm_ms = attn_ms = ln_ms = other_ms = 0.0
+        launches0 = m.launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            model.embed_image_device(px_dev)
+            model.embed_text_device(tok_dev)
+        e1.record()
+        barrier()
+        launches = m.launch_count() - launches0
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # per-class device time, CUDA events recorded around every kernel of the K timed steps
+        tm = model.last_timing()
+        model.set_profiling(False)
+        gemm_ms, attn_ms, ln_ms, other_ms = tm["gemm"] / K, tm["attention"] / K, tm["layernorm"] / K, tm["other"] / K
+        gemm_launches = (arch.vision.layers * 4 + 1) + arch.text.layers * 4
+
+        # e2e through the drop-in mapper contract: pinned host tensors in, numpy fp16 out
+        item = {"image_tensor": px_host, "text_tokens": tok_host, "image_filename": None, "text": None, "metadata": None}
+
+        def step_e2e():
+            a = model.embed_image(item["image_tensor"])
+            b = model.embed_text(item["text_tokens"])
+            return a, b
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        Ke = max(2, min(K, 5))
+        for _ in range(Ke):
+            ei, et = step_e2e()
+        torch.cuda.synchronize(dev)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        clocks = sampler.stop() if rank == 0 else None
+
+        ms_per_step = ms_total / K
+        value = world * B / (ms_per_step / 1e3)
+        gemm_flops = (fl["image_gemm"] + fl["text_gemm"]) * B
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+        out.update({
+            "metric": "ViT-L/14 embeds/s (image+text pairs/s)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 LN/softmax/norm; fp16 output)", "data": "synthetic",
+            "config": {"workload": "ViT-L/14 image+text inference, synthetic 224^2, batch %d per GPU (BASELINE configs[1])" % B,
+                       "global_batch": B * world, "parallelism": "dp%d (independent replicas, no collective)" % world,
+                       "weights": "seeded random init", "l2": "inputs (616.6 MB/step) larger than L2"},
+            "e2e": {"value": world * B * Ke / e2e_s, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(px_host.numel() * 4 + tok_host.numel() * 8),
+                    "d2h_bytes_per_step": int(ei.nbytes + et.nbytes), "steps": Ke,
+                    "api": "B200Clip.embed_image/embed_text (what ClipMapper.__call__ runs), pinned host tensors"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gemm_bf16_tcgen05_kernel", "launches_per_step": gemm_launches,
+                         "peak_source": "%s bf16_tflops_sustained" % peaks["_source"],
+                         "flops_per_step": gemm_flops, "gemm_ms_per_step": gemm_ms},
+            "breakdown_ms_per_step": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "other": other_ms},
+            "model_flops": {"per_pair": fl["pair"], "mfu_of_step": fl["pair"] * B / (ms_per_step / 1e3) / 1e12 / peak},
+        })
+        if clocks is not None:
+            out["clocks"] = clocks
+        del model, px_dev, tok_dev
+        torch.cuda.empty_cache()
+
+    if args.workload == "knn" or not args.no_knn:
+        out["knn" if args.workload == "vitl14" else "knn_main"] = run_knn(args, m, torch, dist, dev, local, rank, world, peaks, barrier, max_over_ranks)
+        if args.workload == "knn":
+            kn = out.pop("knn_main")
+            out.update({"metric": "brute-force kNN QPS (%dx768 fp16 per GPU, nq=%d, top-%d)" % (kn["rows_per_gpu"], kn["nq"], kn["k"]),
+                        "value": kn["qps"], "unit": "queries/s", "n_gpus": world, "steps": kn["steps"], "warmup": kn["warmup"],
+                        "ms_per_step": kn["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                        "dtype": "f16 rows, f32 accumulate", "data": "synthetic", "config": {"workload": kn["workload"]},
+                        "roofline": kn["roofline"], "e2e": kn["e2e"], "gpu_launches": kn["gpu_launches"], "knn": kn})
+
+    if rank == 0 and world >= 1:
+        if args.workload == "vitl14" and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline_embed(arch_name, args.cpu_sample)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_knn(args, m, torch, dist, dev, local, rank, world, peaks, barrier, max_over_ranks):
+    from clip_retrieval_b200.index import synth_rows
+
+    d, k, nq = 768, 40, args.knn_nq
+    free, total = torch.cuda.mem_get_info(dev)
+    rows = args.knn_rows
+    cap = int((free - (6 << 30)) // (d * 2))
+    if rows > cap:
+        rows = cap
+    lo = rank * rows
+    idx = m.B200FlatIndex(d, device=local)
+    idx.reserve(rows)
+    spec = m.SynthSpec(seed=1234)
+    step_rows = 8_000_000
+    for r0 in range(0, rows, step_rows):
+        idx.add_synthetic(min(step_rows, rows - r0), spec, row0=lo + r0)
+    idx.id_base = lo
+    sh = m.ShardedIndex(idx, device=dev)
+    q = synth_rows(nq, d, m.SynthSpec(seed=4321), dtype="float32", device=local)
+    q1 = q[:1].contiguous()
+    Wk, Kk = 1, max(1, args.knn_steps)
+    for _ in range(Wk):
+        sh.search_device(q, k)
+    launches0 = m.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scan_ms = 0.0
+    scan_launches = 0
+    for _ in range(Kk):
+        sh.search_device(q, k)
+    e1.record()
+    barrier()
+    launches = m.launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1)) / Kk
+    s_ms, s_n = idx.last_scan_ms()
+    # serving shape: one query at a time (clip_back.py:362 issues nq=1)
+    for _ in range(3):
+        sh.search_device(q1, k)
+    barrier()
+    e0.record()
+    n1 = 20
+    for _ in range(n1):
+        sh.search_device(q1, k)
+    e1.record()
+    barrier()
+    ms1 = max_over_ranks(e0.elapsed_time(e1)) / n1
+    s1_ms, s1_n = idx.last_scan_ms()
+    # e2e: host numpy in/out through the FAISS-style call
+    qh = q.cpu().numpy()
+    t0 = time.perf_counter()
+    D, I = sh.search(qh, k)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    peak = peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+    bytes_per_launch = rows * d * 2
+    ach1 = bytes_per_launch / (s1_ms / s1_n / 1e3) / 1e9
+    achN = bytes_per_launch / (s_ms / s_n / 1e3) / 1e9
+    return {
+        "workload": "brute-force cosine kNN, %d x %d fp16 rows per GPU (%d GPUs, range-sharded), %d queries, top-%d (BASELINE configs[2])" % (rows, d, world, nq, k),
+        "rows_per_gpu": rows, "rows_total": rows * world, "nq": nq, "k": k, "steps": Kk, "warmup": Wk,
+        "qps": nq / (ms / 1e3), "ms_per_step": ms, "single_query_ms": ms1, "single_query_qps": 1e3 / ms1,
+        "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(D.nbytes + I.nbytes)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "traffic": None,
+                     "kernel": "flat_scan_kernel<1,3> (nq=1 serving shape)", "bytes_per_launch": bytes_per_launch,
+                     "batch_pass": {"achieved": achN, "frac": achN / peak, "launches_per_step": s_n},
+                     "peak_source": "%s hbm_gbs" % peaks["_source"]},
+    }
+
+
+# ---- the reference arm: the CPU oracle port of the same workload ---------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, K, W = args.batch, args.steps, args.warmup
+    n = max(2, min(args.cpu_sample, 32))
+    steps = max(1, min(K, 3))
+    best = None
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        cb = cpu_baseline_embed("ViT-L/14", n)
+        best = cb if best is None or cb["value"] > best["value"] else best
+        if time.perf_counter() - t_all > 150:
+            break
+    print(json.dumps({
+        "impl": "reference", "metric": "ViT-L/14 embeds/s (image+text pairs/s)", "value": best["value"], "unit": "pairs/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 1, "ms_per_step": 1e3 * n / best["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-L/14 image+text inference, synthetic 224^2 (bounded sample of %d pairs per step of the batch-%d workload)" % (n, B)},
+        "cpu_baseline": best,
+        "e2e": {"value": best["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference's own path (all_clip/open_clip) cannot be installed offline; this is the CPU oracle port (oracle/clip_ref.py)",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="vitl14", choices=["vitl14", "knn"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--knn-rows", type=int, default=100_000_000)
+    ap.add_argument("--knn-nq", type=int, default=1000)
+    ap.add_argument("--knn-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

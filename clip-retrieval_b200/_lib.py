@@ -103,6 +103,8 @@ PROTOTYPES = {
     "b200_clip_encode_text": (_i, [_vp, _vp, _i, _vp, _i, _i]),
     "b200_clip_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "b200_clip_set_profiling": (_i, [_vp, _i]),
+    "b200_layernorm_bf16_device": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "b200_attention_bf16_device": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_gemm_bf16_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -395,7 +395,6 @@ static int encode_device(b200_clip* m, const void* d_in, int B, void* d_out, int
   B200_CHECK(m->loaded, B200_ERR_STATE, "encode: weights not loaded");
   B200_CHECK(out_dtype == B200_OUT_F16 || out_dtype == B200_OUT_F32, B200_ERR_INVALID, "encode: out_dtype %d", out_dtype);
   DeviceGuard g(m->device);
-  m->span_used = 0;
   m->last_launches = 0;
   const int mb = m->cfg.max_batch;
   const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
@@ -447,13 +446,28 @@ int b200_clip_encode_text(b200_clip* m, const int64_t* h_tokens, int B, void* h_
   return encode_host(m, h_tokens, B, h_out, out_dtype, normalize, false);
 }
 
+int b200_layernorm_bf16_device(const void* d_in, void* d_out, const float* d_gamma, const float* d_beta, int64_t rows,
+                               int w, int device, void* stream) {
+  B200_CHECK(d_in && d_out && d_gamma && d_beta && rows >= 0, B200_ERR_INVALID, "layernorm: bad argument");
+  DeviceGuard g(device);
+  return layernorm_rows((const __nv_bfloat16*)d_in, w, (__nv_bfloat16*)d_out, w, d_gamma, d_beta, rows, w,
+                        (cudaStream_t)stream);
+}
+int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int heads, int w, int causal, int device,
+                               void* stream) {
+  B200_CHECK(d_qkv && d_out && B >= 0 && T >= 1, B200_ERR_INVALID, "attention: bad argument");
+  DeviceGuard g(device);
+  return attention((const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, (cudaStream_t)stream);
+}
+
 int b200_clip_set_profiling(b200_clip* m, int on) {
   B200_CHECK(m, B200_ERR_INVALID, "set_profiling: null handle");
   m->profiling = on != 0;
+  m->span_used = 0;
   return B200_OK;
 }
 
-int b200_clip_last_timing(const b200_clip* m, float* ms_by_class, int* launches) {
+int b200_clip_last_timing(b200_clip* m, float* ms_by_class, int* launches) {
   B200_CHECK(m && ms_by_class, B200_ERR_INVALID, "last_timing: null argument");
   DeviceGuard g(m->device);
   for (int i = 0; i < 4; i++) ms_by_class[i] = 0.f;
@@ -464,7 +478,8 @@ int b200_clip_last_timing(const b200_clip* m, float* ms_by_class, int* launches)
     B200_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
     if (s.cls >= 0 && s.cls < 4) ms_by_class[s.cls] += t;
   }
-  if (launches) *launches = m->last_launches;
+  if (launches) *launches = m->span_used;
+  m->span_used = 0;
   return B200_OK;
 }
 

