@@ -308,6 +308,16 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
   return B200_OK;
 }
 
+int launch_topk_select(const unsigned long long* in, int64_t in_stride_q, int64_t M, int k, int C,
+                       unsigned long long* out, int64_t out_stride_q, int slices, int nq, cudaStream_t st) {
+  const size_t sel_smem = (size_t)C * 8;
+  if (sel_smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  topk_select_kernel<<<dim3(slices, nq), 1024, sel_smem, st>>>(in, in_stride_q, M, k, C, out, out_stride_q);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
 int decode_keys(const unsigned long long* keys, int64_t count, int64_t id_base, const uint32_t* slot_to_id, float* D,
                 int64_t* I, cudaStream_t st) {
   if (count == 0) return B200_OK;

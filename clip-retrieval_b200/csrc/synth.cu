@@ -57,6 +57,45 @@ __global__ void synth_rows_kernel(OutT* __restrict__ out, int64_t n, int d, int6
   }
 }
 
+// Same rows, written in a permuted order: out[p] = row (row0 + src_rows[p])  (IVF list order).
+__global__ void synth_rows_indirect_kernel(__half* __restrict__ out, const uint32_t* __restrict__ src_rows, int64_t n,
+                                           int d, int64_t row0, b200_synth_spec spec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = warp; p < n; p += nwarps) {
+    const uint64_t row = (uint64_t)(row0 + (int64_t)src_rows[p]);
+    const uint64_t rk = row_key(spec.seed, row);
+    uint64_t ck = 0;
+    if (spec.clustered) ck = row_key(spec.centroid_seed, list_of_row(spec.centroid_seed, row, spec.nlist));
+    long long ss = 0;
+    for (int j = lane; j < d; j += 32) {
+      int v = noise_at(rk, j);
+      if (spec.clustered) v = spec.cw * noise_at(ck, j) + spec.nw * v;
+      ss += (long long)v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const double norm = sqrt((double)ss);
+    __half* orow = out + p * (int64_t)d;
+    for (int j = lane; j < d; j += 32) {
+      int v = noise_at(rk, j);
+      if (spec.clustered) v = spec.cw * noise_at(ck, j) + spec.nw * v;
+      orow[j] = __float2half_rn((ss == 0) ? 0.0f : (float)((double)v / norm));
+    }
+  }
+}
+
+int synth_rows_indirect_f16(__half* out, const uint32_t* src_rows, int64_t n, int d, int64_t row0,
+                            const b200_synth_spec* spec, cudaStream_t st) {
+  if (n == 0) return B200_OK;
+  int64_t blocks = (n + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  synth_rows_indirect_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, src_rows, n, d, row0, *spec);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
 template <typename OutT>
 int synth_rows(OutT* d_out, int64_t n, int d, int64_t row0, const b200_synth_spec* spec, cudaStream_t st) {
   B200_CHECK(spec != nullptr && d_out != nullptr, B200_ERR_INVALID, "synth_rows: null argument");

@@ -53,12 +53,13 @@ class ShardedIndex:
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
         # the single exchange step: candidates are packed so that one all-gather moves both arrays
-        packed = torch.cat([D.view(torch.int32).reshape(-1), I.view(torch.int32).reshape(-1)])
-        gathered = torch.empty((self.world, packed.numel()), dtype=torch.int32, device=packed.device)
-        self.dist.all_gather_into_tensor(gathered, packed, group=self.group)
-        nD = D.numel()
-        Dg.copy_(gathered[:, :nD].reshape(self.world, *D.shape).view(torch.float32))
-        Ig.copy_(gathered[:, nD:].reshape(self.world, I.shape[0], I.shape[1] * 2).view(torch.int64))
+        packed = torch.cat([I.view(torch.int32).reshape(-1), D.view(torch.int32).reshape(-1)])
+        flat = torch.empty(self.world * packed.numel(), dtype=torch.int32, device=packed.device)
+        self.dist.all_gather_into_tensor(flat, packed, group=self.group)
+        gathered = flat.view(self.world, packed.numel())
+        nI = 2 * I.numel()
+        Ig.copy_(gathered[:, :nI].clone().view(torch.int64).reshape(self.world, *I.shape))
+        Dg.copy_(gathered[:, nI:].clone().view(torch.float32).reshape(self.world, *D.shape))
         return self.merge_fn(Dg, Ig, k)
 
     def search(self, x, k):
