@@ -152,7 +152,7 @@ static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int
   const int bn = gemm_pick_bn(M, l.N, m->sms);
   ep.bias = l.b;
   m->last_launches++;
-  return gemm_bf16_launch(tmA, bn == 256 ? l.tm256 : l.tm128, bn, M, l.N, l.K, ep, m->sms, st);
+  return gemm_bf16_launch(tmA, bn == 256 ? l.tm256 : l.tm128, bn, M, l.N, l.K, ep, m->sms, st);  // pair mode: tm128
 }
 
 static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st) {

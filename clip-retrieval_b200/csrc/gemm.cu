@@ -1,6 +1,8 @@
 // Host side of the tcgen05 GEMM: tensor-map construction, launch, and the stand-alone C-ABI entry.
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include <mutex>
+#include <algorithm>
 
 namespace b200 {
 
@@ -42,7 +44,14 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t row
   return B200_OK;
 }
 
+static bool g_pair_enabled = true;
+void gemm_set_pair_mode(bool on) { g_pair_enabled = on; }
+
+// Column-block choice; GEMM_MODE_PAIR (= 512) selects the CTA-pair kernel (256x256 tiles over two
+// SMs, B operand through the 128-row tensor map) for problems that fill the chip with such tiles.
 int gemm_pick_bn(int M, int N, int sms) {
+  const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+  if (g_pair_enabled && pair_tiles >= 2 * (long)(sms / 2) && N >= 256) return GEMM_MODE_PAIR;
   if (N % 256 != 0 && N % 128 == 0) return 128;
   const long tiles256 = (long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256);
   if (tiles256 < sms && N > 128) return 128;  // small problems: more, narrower tiles
@@ -76,6 +85,21 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
              "gemm: output must be 16-byte aligned with ld %% 8 == 0");
   B200_CHECK(ep.residual == nullptr || (ep.res_ld % 8 == 0 && ((uintptr_t)ep.residual & 15) == 0), B200_ERR_INVALID,
              "gemm: residual must be 16-byte aligned with ld %% 8 == 0");
+  if (bn == GEMM_MODE_PAIR) {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    if (!(configured.load() >> (dev & 63) & 1ull)) {
+      B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     G2_SMEM_BYTES));
+      configured.fetch_or(1ull << (dev & 63));
+    }
+    const long tiles = (long)((M + G2_BM - 1) / G2_BM) * ((N + G2_BN - 1) / G2_BN);
+    const int pairs = (int)std::min<long>(tiles, sms / 2);
+    gemm_bf16_tcgen05_pair_kernel<<<2 * pairs, GEMM_THREADS, G2_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep);
+    B200_LAUNCH_OK();
+    return B200_OK;
+  }
   if (bn == 256) return launch_bn<256>(tmA, tmB, M, N, K, ep, sms, st);
   if (bn == 128) return launch_bn<128>(tmA, tmB, M, N, K, ep, sms, st);
   set_error("gemm: unsupported column block %d", bn);
@@ -95,7 +119,8 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   const int bn = gemm_pick_bn(M, N, sms);
   CUtensorMap tmA, tmB;
   B200_TRY(make_tmap_2d(&tmA, d_A, 1, (uint64_t)M, (uint64_t)K, (uint64_t)K, GEMM_BM, GEMM_BK));
-  B200_TRY(make_tmap_2d(&tmB, d_W, 1, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, GEMM_BK));
+  B200_TRY(make_tmap_2d(&tmB, d_W, 1, (uint64_t)N, (uint64_t)K, (uint64_t)K, bn == GEMM_MODE_PAIR ? 128u : (uint32_t)bn,
+                        GEMM_BK));
   GemmEpilogue ep;
   ep.bias = d_bias;
   ep.residual = (const __nv_bfloat16*)d_residual;
@@ -104,4 +129,9 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   ep.out_ld = N;
   ep.act = act;
   return gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream);
+}
+
+extern "C" int b200_gemm_set_pair_mode(int on) {
+  b200::gemm_set_pair_mode(on != 0);
+  return B200_OK;
 }

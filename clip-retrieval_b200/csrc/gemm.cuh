@@ -25,6 +25,7 @@ constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_GROUP_M = 16;
 
 enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU = 2 };
+constexpr int GEMM_MODE_PAIR = 512;  // gemm_pick_bn result selecting the cta_group::2 kernel (gemm2.cuh)
 
 struct GemmEpilogue {
   const float* bias = nullptr;              // [N] fp32 or null
@@ -141,6 +142,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
@@ -171,6 +173,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (acc == 0) acc_phase ^= 1;
       }
     }
+    __syncwarp();
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
@@ -252,5 +255,6 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
 // Pick the column-block width for a GEMM with N output columns (256, or 128 when N % 256 != 0 or the
 // grid would be under-filled).
 int gemm_pick_bn(int M, int N, int sms);
+void gemm_set_pair_mode(bool on);
 
 }  // namespace b200

@@ -1,0 +1,202 @@
+// tcgen05 GEMM on CTA PAIRS (cta_group::2): the large-shape variant of gemm.cuh.
+//
+// Why: with one CTA per 128x256 tile every SM pulls 48 KB of operands from L2 per 64-wide k-block
+// (96 B/clk/SM at the MMA rate) — more than the L2 can feed 148 SMs.  A pair of CTAs on one TPC
+// computes a 256x256 tile with ONE tcgen05.mma.cta_group::2 per k-step: each CTA stages its own
+// 128 rows of A and only HALF of the B tile (128 of the 256 weight rows); the tensor core reads
+// both halves across the pair.  Operand traffic drops to 32 KB per k-block per SM and the ring
+// deepens to 6 stages in the same shared memory.
+//
+// Roles per CTA: warp 0 TMA producer (its A half + its B half; completion bytes are credited to
+// the leader's full barrier), warp 1 = MMA issuer in the leader CTA only, warps 2..5 epilogue over
+// this CTA's 128 accumulator rows.  tcgen05.commit multicasts "slot free" / "accumulator ready" to
+// the barriers of both CTAs; epilogue warps of both CTAs release the accumulator stage on the
+// leader's barrier (remote mbarrier arrive for the second CTA).
+#pragma once
+#include "gemm.cuh"
+
+namespace b200 {
+
+constexpr int G2_BM = 256;          // rows per pair tile (128 per CTA)
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;   // 16 KB
+constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;   // 16 KB (half of the 256-wide B tile)
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_BN * 4 + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
+                              int N, int K, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = base;
+  uint8_t* sB = base + G2_STAGES * G2_A_BYTES;
+  float* s_bias = reinterpret_cast<float*>(base + G2_STAGES * G2_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + G2_BN);
+  uint64_t* empty = full + G2_STAGES;
+  uint64_t* tfull = empty + G2_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int mb = (M + G2_BM - 1) / G2_BM, nb = (N + G2_BN - 1) / G2_BN, kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles = mb * nb;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < G2_STAGES; s++) {
+        ptx::mbar_init(&full[s], 2);   // one arrive per CTA's producer (used in the leader only)
+        ptx::mbar_init(&empty[s], 1);  // multicast commit from the leader's MMA
+      }
+      for (int a = 0; a < 2; a++) {
+        ptx::mbar_init(&tfull[a], 1);
+        ptx::mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc_pair(s_tmem, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0_remote = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+      for (int tile = pair; tile < tiles; tile += npairs) {
+        int m_blk, n_blk;
+        gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
+        for (int kbi = 0; kbi < kb; kbi++) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, &full[stage], kbi * GEMM_BK,
+                                m_blk * G2_BM + (int)rank * 128);
+          ptx::tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, &full[stage], kbi * GEMM_BK,
+                                n_blk * G2_BN + (int)rank * 128);
+          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+          else ptx::mbar_arrive_cluster(full0_remote + (uint32_t)stage * 8u);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(G2_BM, G2_BN, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < tiles; tile += npairs) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        for (int kbi = 0; kbi < kb; kbi++) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + stage * G2_A_BYTES));
+          const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + stage * G2_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; k++)
+            ptx::umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kbi | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_pair(&empty[stage], 3);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_pair(&tfull[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (warps 2..5 of both CTAs) ----------------
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
+    for (int tile = pair; tile < tiles; tile += npairs) {
+      int m_blk, n_blk;
+      gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
+      const int n0 = n_blk * G2_BN;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int j = et; j < G2_BN; j += 128) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+
+      const int row = m_blk * G2_BM + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = row < M;
+      int64_t out_row = row;
+      if (ep.out_group > 0) out_row = (int64_t)(row / ep.out_group) * (ep.out_group + 1) + 1 + row % ep.out_group;
+      int64_t res_row = row;
+      if (ep.res_row_mod > 0) res_row = ep.res_row_off + row % ep.res_row_mod;
+      __nv_bfloat16* out_ptr = ep.out + out_row * ep.out_ld + n0;
+      const __nv_bfloat16* res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
+
+#pragma unroll 1
+      for (int c = 0; c < G2_BN / 32; c++) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+        ptx::tmem_ld_wait();
+        if (c == G2_BN / 32 - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&tempty[acc]);
+            else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int col = c * 32 + g * 8;
+            if (n0 + col < N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r[g * 8 + j]) + s_bias[col + j], ep.act);
+              if (res_ptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr + col);
+                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z),
+                             dd = unpack_bf16x2(rr.w);
+                v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+                v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(out_ptr + col) = o;
+            }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace b200

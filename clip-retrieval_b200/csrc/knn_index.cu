@@ -306,6 +306,12 @@ int b200_index_set_nprobe(b200_index* idx, int nprobe) {
 }
 int b200_index_get_nprobe(const b200_index* idx) { return idx ? idx->nprobe : -1; }
 
+int b200_index_set_tensor_scan(b200_index* idx, int on) {
+  B200_CHECK(idx, B200_ERR_INVALID, "set_tensor_scan: null index");
+  idx->use_mma = on != 0;
+  return B200_OK;
+}
+
 int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids) {
   B200_CHECK(idx && h_sizes, B200_ERR_INVALID, "ivf_lists: null argument");
   B200_CHECK(idx->nlist > 0, B200_ERR_STATE, "ivf_lists: not an IVF index");

@@ -1,0 +1,322 @@
+// Search path, batched exhaustive scan on the tensor cores: the same answer as flat_scan_kernel
+// (knn_scan.cu) when many queries arrive together (BASELINE configs[2]: 1000 queries, top-40), with
+// the index read once per 128 queries instead of once per 4.
+//
+//   S[row, q] = sum_j X[row, j] * Q[q, j]          X fp16 rows (HBM), Q fp32 queries
+//
+// tcgen05 kind::f16 needs fp16 operands, and rounding the query to fp16 (2^-11 relative) would swap
+// near-tied neighbours, so each fp32 query is split into two fp16 rows: hi = fp16(q) and
+// lo = fp16((q - hi) * 2^11); the products with fp16 rows are exact in fp32, the two partial sums
+// are accumulated in separate TMEM columns and recombined as s = s_hi + s_lo * 2^-11 in the
+// epilogue (22 significant bits of the query: below the fp32 accumulation noise already accepted
+// for the FMA kernel).
+//
+// Structure = the GEMM core (gemm.cuh): warp 0 TMA producer (X box 128x64, Q' box 256x64, 128B
+// swizzle, 4-stage ring), warp 1 MMA issuer (128x256x16, two TMEM accumulator stages), warps 2..5
+// epilogue.  A CTA owns whole 128-row tiles (tile = cta + i*grid) and walks all query groups of a
+// tile back to back, so the X tile is re-read from L2, not HBM.  Epilogue: thread = row; a score
+// that reaches the query's current threshold is appended to the (CTA, query) candidate buffer
+// (atomic counter in shared memory, buffer in global/L2); buffers are compacted to their k best by
+// the epilogue warps between tiles, which raises the threshold.  A final select merges the CTAs.
+// Roofline: tensor pipe (4*N*d*nq flops with the split) for large nq, HBM (N*d*2 bytes per 128
+// queries) below ~64 queries per pass.
+#include "index.cuh"
+#include "topk.cuh"
+#include "ptx.cuh"
+#include "gemm.cuh"
+#include <algorithm>
+
+namespace b200 {
+
+int launch_topk_select(const unsigned long long* in, int64_t in_stride_q, int64_t M, int k, int C,
+                       unsigned long long* out, int64_t out_stride_q, int slices, int nq, cudaStream_t st);
+
+constexpr int MS_BM = 128;       // rows per tile
+constexpr int MS_QG = 128;       // queries per group (256 MMA columns: hi | lo)
+constexpr int MS_BN = 256;
+constexpr int MS_BK = 64;
+constexpr int MS_STAGES = 4;
+constexpr int MS_CAP = 256;      // candidate buffer entries per (CTA, query)
+constexpr int MS_KMAX = 128;     // k supported by this path (CAP - BM)
+constexpr int MS_THREADS = 192;
+constexpr int MS_A_BYTES = MS_BM * MS_BK * 2;
+constexpr int MS_B_BYTES = MS_BN * MS_BK * 2;
+constexpr int MS_STAGE_BYTES = MS_A_BYTES + MS_B_BYTES;
+
+// fp32 queries -> fp16 [groups*256, d]: row g*256 + c (c < 128) = hi of query g*128 + c,
+// row g*256 + 128 + c = lo * 2^11 of the same query; padding queries are zero rows.
+__global__ void split_queries_kernel(const float* __restrict__ Q, int nq, int d, __half* __restrict__ Qp, int groups) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)groups * MS_QG * d;
+  if (i >= total) return;
+  const int q = (int)(i / d), j = (int)(i - (int64_t)q * d);
+  const int g = q / MS_QG, c = q - g * MS_QG;
+  float v = q < nq ? Q[(int64_t)q * d + j] : 0.0f;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+  Qp[((int64_t)g * MS_BN + c) * d + j] = hi;
+  Qp[((int64_t)g * MS_BN + MS_QG + c) * d + j] = lo;
+}
+
+// Keep the k best of a (CTA, query) candidate buffer; returns the new threshold score.
+// One warp; up to MS_CAP keys live in registers (8 per lane).
+__device__ __forceinline__ float compact_buffer(unsigned long long* buf, int count, int k, int lane) {
+  unsigned long long v[MS_CAP / 32];
+#pragma unroll
+  for (int i = 0; i < MS_CAP / 32; i++) {
+    const int j = i * 32 + lane;
+    v[i] = j < count ? buf[j] : 0ull;
+  }
+  __syncwarp();
+  unsigned long long last = 0ull;
+  for (int r = 0; r < k; r++) {
+    unsigned long long m = v[0];
+    int mi = 0;
+#pragma unroll
+    for (int i = 1; i < MS_CAP / 32; i++)
+      if (v[i] > m) { m = v[i]; mi = i; }
+    unsigned long long wm = m;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(FULL, wm, o);
+      wm = t > wm ? t : wm;
+    }
+    // keys are unique (ids differ) unless zero; the first lane holding the maximum retires it
+    const unsigned who = __ballot_sync(FULL, m == wm);
+    if (wm != 0ull && lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int i = 0; i < MS_CAP / 32; i++)
+        if (i == mi) v[i] = 0ull;
+    }
+    if (lane == 0) buf[r] = wm;
+    last = wm;
+  }
+  for (int j = k + lane; j < MS_CAP; j += 32) buf[j] = 0ull;
+  __syncwarp();
+  return last != 0ull ? key_score(last) : -INFINITY;
+}
+
+__global__ void __launch_bounds__(MS_THREADS, 1)
+scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n, int d,
+                int nq, int groups, int k, unsigned long long* __restrict__ cand /* [grid][groups*128][CAP] */,
+                unsigned long long* __restrict__ dense /* [nq][grid][k] */) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = base;
+  uint8_t* sB = base + MS_STAGES * MS_A_BYTES;
+  float* s_thr = reinterpret_cast<float*>(base + MS_STAGES * MS_STAGE_BYTES);  // [groups*128]
+  int* s_cnt = reinterpret_cast<int*>(s_thr + groups * MS_QG);                 // [groups*128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + groups * MS_QG);
+  uint64_t* empty = full + MS_STAGES;
+  uint64_t* tfull = empty + MS_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_tiles = (n + MS_BM - 1) / MS_BM;
+  const int kb = (d + MS_BK - 1) / MS_BK;
+
+  for (int i = threadIdx.x; i < groups * MS_QG; i += blockDim.x) {
+    s_thr[i] = -INFINITY;
+    s_cnt[i] = 0;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmQ);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < MS_STAGES; s++) {
+        ptx::mbar_init(&full[s], 1);
+        ptx::mbar_init(&empty[s], 1);
+      }
+      for (int a = 0; a < 2; a++) {
+        ptx::mbar_init(&tfull[a], 1);
+        ptx::mbar_init(&tempty[a], 4);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(s_tmem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+        for (int g = 0; g < groups; g++) {
+          for (int kbi = 0; kbi < kb; kbi++) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[stage], MS_STAGE_BYTES);
+            ptx::tma_load_2d(sA + stage * MS_A_BYTES, &tmX, &full[stage], kbi * MS_BK, (int32_t)(rt * MS_BM));
+            ptx::tma_load_2d(sB + stage * MS_B_BYTES, &tmQ, &full[stage], kbi * MS_BK, g * MS_BN);
+            if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(MS_BM, MS_BN, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+        for (int g = 0; g < groups; g++) {
+          ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * MS_BN;
+          for (int kbi = 0; kbi < kb; kbi++) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + stage * MS_A_BYTES));
+            const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + stage * MS_B_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < MS_BK / 16; kk++)
+              ptx::umma_f16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kbi | kk) != 0 ? 1u : 0u);
+            ptx::umma_commit(&empty[stage]);
+            if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: thresholded append + compaction ----------------
+    const int q4 = warp & 3;
+    const int ew = warp - 2;  // 0..3
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    unsigned long long* my_cand = cand + (int64_t)blockIdx.x * groups * MS_QG * MS_CAP;
+    for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+      const int64_t row = rt * MS_BM + q4 * 32 + lane;
+      const bool row_ok = row < n;
+      for (int g = 0; g < groups; g++) {
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t tbase = tmem_base + acc * MS_BN + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < MS_QG / 32; c++) {
+          uint32_t hi[32], lo[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
+          ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
+          ptx::tmem_ld_wait();
+          if (c == MS_QG / 32 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int q = g * MS_QG + c * 32 + j;
+              const float s = fmaf(__uint_as_float(lo[j]), 1.0f / 2048.0f, __uint_as_float(hi[j]));
+              if (s >= s_thr[q] && q < nq) {
+                const int pos = atomicAdd(&s_cnt[q], 1);
+                if (pos < MS_CAP) my_cand[(int64_t)q * MS_CAP + pos] = make_key(s, (uint32_t)row);
+              }
+            }
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        // compaction of this group's buffers that could overflow during the next tile
+        __threadfence_block();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int qq = ew; qq < MS_QG; qq += 4) {
+          const int q = g * MS_QG + qq;
+          const int cnt = s_cnt[q];
+          if (cnt > MS_CAP - MS_BM) {
+            const float thr = compact_buffer(my_cand + (int64_t)q * MS_CAP, min(cnt, MS_CAP), k, lane);
+            if (lane == 0) {
+              s_cnt[q] = min(cnt, k);
+              s_thr[q] = thr;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    // final pass: every (CTA, query) buffer reduced to its k best and written densely for the merge
+    for (int q = ew; q < nq; q += 4) {
+      unsigned long long* buf = my_cand + (int64_t)q * MS_CAP;
+      const int cnt = s_cnt[q];
+      if (cnt > k) compact_buffer(buf, min(cnt, MS_CAP), k, lane);
+      unsigned long long* o = dense + ((int64_t)q * gridDim.x + blockIdx.x) * k;
+      for (int j = lane; j < k; j += 32) o[j] = buf[j];
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols);
+
+// Batched scan entry: same contract as scan_topk_keys (knn_scan.cu).
+int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const float* d_q, int nq, int k,
+                       unsigned long long* d_keys_out, cudaStream_t st) {
+  const int d = idx->d;
+  B200_CHECK(k <= MS_KMAX, B200_ERR_UNSUPPORTED, "mma scan: k=%d > %d", k, MS_KMAX);
+  B200_CHECK(n < (1ll << 31), B200_ERR_UNSUPPORTED, "mma scan: at most 2^31 rows per shard");
+  const int grid = idx->sms;
+  const int QMAX = 1024;  // queries per launch (thresholds/counters live in shared memory)
+  for (int q0 = 0; q0 < nq; q0 += QMAX) {
+    const int nqb = std::min(QMAX, nq - q0);
+    const int groups = (nqb + MS_QG - 1) / MS_QG;
+    const size_t qp_bytes = ((size_t)groups * MS_BN * d * sizeof(__half) + 255) & ~(size_t)255;
+    const size_t cand_bytes = (size_t)grid * groups * MS_QG * MS_CAP * 8;
+    const size_t dense_bytes = (size_t)nqb * grid * k * 8;
+    void* ws = nullptr;
+    B200_TRY(index_ws(idx, 0, qp_bytes + cand_bytes + dense_bytes, &ws));
+    __half* Qp = (__half*)ws;
+    unsigned long long* cand = (unsigned long long*)((char*)ws + qp_bytes);
+    unsigned long long* dense = (unsigned long long*)((char*)ws + qp_bytes + cand_bytes);
+    B200_CUDA(cudaMemsetAsync(cand, 0, cand_bytes, st));
+    {
+      const int64_t total = (int64_t)groups * MS_QG * d;
+      split_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q + (size_t)q0 * d, nqb, d, Qp, groups);
+      B200_LAUNCH_OK();
+    }
+    CUtensorMap tmX, tmQ;
+    B200_TRY(make_tmap_2d(&tmX, rows, 0, (uint64_t)n, (uint64_t)d, (uint64_t)d, MS_BM, MS_BK));
+    B200_TRY(make_tmap_2d(&tmQ, Qp, 0, (uint64_t)groups * MS_BN, (uint64_t)d, (uint64_t)d, MS_BN, MS_BK));
+    const size_t smem = (size_t)MS_STAGES * MS_STAGE_BYTES + (size_t)groups * MS_QG * 8 + 256 + 1024;
+    B200_CUDA(cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((int)idx->ev.size() < idx->ev_used + 2) {
+      cudaEvent_t a, b;
+      B200_CUDA(cudaEventCreate(&a));
+      B200_CUDA(cudaEventCreate(&b));
+      idx->ev.push_back(a);
+      idx->ev.push_back(b);
+    }
+    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
+    scan_mma_kernel<<<grid, MS_THREADS, smem, st>>>(tmX, tmQ, n, d, nqb, groups, k, cand, dense);
+    B200_LAUNCH_OK();
+    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
+    idx->ev_used += 2;
+    idx->last_scan_launches++;
+    // merge the per-CTA lists: grid*k candidates per query
+    const int64_t M = (int64_t)grid * k;
+    int C = 2048;
+    while (C < 2 * k) C <<= 1;
+    B200_TRY(launch_topk_select(dense, M, M, k, C, d_keys_out + (size_t)q0 * k, k, 1, nqb, st));
+  }
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -259,9 +259,15 @@ static int plan_scan(const b200_index* idx, int k, int nq, ScanPlan* p) {
   return B200_OK;
 }
 
+int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const float* d_q, int nq, int k,
+                       unsigned long long* d_keys_out, cudaStream_t st);
+
 int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* d_q, int nq, int k,
                    unsigned long long* d_keys_out, cudaStream_t st) {
   const int d = idx->d;
+  // many queries at once: one tensor-core pass per 128 queries instead of one FMA pass per 4
+  if (idx->use_mma && nq > 4 && k <= 128 && n >= 4096 && n < (1ll << 31) && d >= 64)
+    return scan_topk_keys_mma(idx, rows, n, d_q, nq, k, d_keys_out, st);
   ScanPlan p;
   B200_TRY(plan_scan(idx, k, nq, &p));
   const int64_t total_warps = (int64_t)p.grid * (p.threads / 32);

@@ -176,6 +176,10 @@ class _IndexBase:
             )
         return (D, I, R) if reconstruct else (D, I)
 
+    def set_tensor_scan(self, on):
+        """Batched queries use the tcgen05 scan by default; False forces the FMA scan."""
+        check(lib.b200_index_set_tensor_scan(self._h, 1 if on else 0), "set_tensor_scan")
+
     def last_scan_ms(self):
         ms = C.c_float(0)
         n = C.c_int(0)

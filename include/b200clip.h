@@ -99,6 +99,9 @@ int b200_index_set_id_base(b200_index* idx, int64_t id_base);
  * (clip_back.py:357-361,368-369). */
 int b200_index_set_nprobe(b200_index* idx, int nprobe);
 int b200_index_get_nprobe(const b200_index* idx);
+/* Batched queries (nq > 4, k <= 128) go through the tcgen05 scan by default; 0 forces the FMA scan
+ * (kept for A/B measurements and parity tests between the two paths). */
+int b200_index_set_tensor_scan(b200_index* idx, int on);
 /* IVF introspection used by ivf_metadata_ordering.get_old_to_new_mapping
  * (ivf_metadata_ordering.py:46-64): sizes[nlist] and, list after list, the ids in list order. */
 int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
@@ -183,6 +186,10 @@ int b200_clip_set_profiling(b200_clip* m, int on);
  *               (+ residual[M,N] bf16 | NULL).  act: 0 none, 1 quick_gelu, 2 gelu(erf). */
 int b200_gemm_bf16_device(const void* d_A, const void* d_W, const float* d_bias, const void* d_residual,
                           void* d_C, int M, int N, int K, int act, int device, void* stream);
+
+/* Large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles) by default; 0 forces the
+ * single-CTA 128x256 kernel for every shape (A/B measurements, parity between the two kernels). */
+int b200_gemm_set_pair_mode(int on);
 
 /* Stand-alone entries of the two other embed kernels, for their parity tests:
  * LayerNorm (eps 1e-5) over rows of `w` bf16 values; multi-head attention over a fused qkv buffer

@@ -33,6 +33,8 @@ def _ref(A, W, b, R, act):
         (130, 520, 328, 1, True, True),       # N, K not multiples of the tile: TMA zero fill + predication
         (4112, 4096, 1024, 1, True, False),
         (4112, 1024, 4096, 0, True, True),
+        (20001, 3072, 1024, 1, True, True),   # CTA-pair kernel (256x256 tiles), ragged M
+        (19000, 1000, 520, 2, True, True),    # CTA-pair kernel, N and K tails
     ],
 )
 def test_gemm_matches_fp32_reference(M, N, K, act, bias, res):

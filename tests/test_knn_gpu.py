@@ -196,3 +196,24 @@ def test_full_size_properties_sharded_idempotent(b200):
         rows = np.stack([synth_ref.rows_f16(1, d, int(i), seed=5)[0] for i in ids[q, :5]])
         s = rows.astype(np.float64) @ Q[q].cpu().numpy().astype(np.float64)
         np.testing.assert_allclose(D1[q, :5].cpu().numpy(), s, atol=TOL)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("nq,k,n,d", [(5, 40, 4096, 768), (64, 40, 60000, 768), (130, 128, 50021, 768), (300, 1, 33000, 512),
+                                      (1000, 40, 150000, 768), (17, 40, 20000, 1024)])
+def test_tensor_scan_matches_oracle_and_fma_scan(b200, nq, k, n, d):
+    """The tcgen05 batch scan (fp32 query split into fp16 hi/lo) against the float64 ranking and
+    against the FMA scan of the same index."""
+    X = synth_ref.rows_f16(n, d)
+    Q = _queries(nq, d)
+    idx = b200.B200FlatIndex(d)
+    idx.add(X)
+    D, I = idx.search(Q, k)                 # nq > 4, k <= 128 -> tensor path
+    ok, msg, strict = knn_ref.check_topk(D, I, knn_ref.scores_f64(X, Q), k, tol=TOL)
+    assert ok, msg
+    idx.set_tensor_scan(False)
+    Df, If = idx.search(Q, k)
+    ok, msg, _ = knn_ref.check_topk(Df, If, knn_ref.scores_f64(X, Q), k, tol=TOL)
+    assert ok, msg
+    np.testing.assert_allclose(D, Df, atol=TOL)
+    assert (I == If).mean() > 0.995         # ids agree except across near-ties

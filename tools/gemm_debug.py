@@ -71,6 +71,9 @@ def run(M, N, K, act=0, bias=True, res=True, time_it=False):
 
 if __name__ == "__main__":
     ok = True
+    if len(sys.argv) > 1:
+        lib.b200_gemm_set_pair_mode(int(sys.argv[1]))
+        print("pair mode", sys.argv[1])
     ok &= run(128, 256, 64, bias=False, res=False)
     ok &= run(128, 256, 256, bias=False, res=False)
     ok &= run(256, 512, 128, bias=True, res=False)
@@ -81,5 +84,8 @@ if __name__ == "__main__":
     ok &= run(16448, 4096, 1024, act=1, time_it=True)
     ok &= run(16448, 1024, 4096, act=0, time_it=True)
     ok &= run(65792, 3072, 1024, act=0, res=False, time_it=True)
+    ok &= run(263168, 1024, 1024, act=0, res=True, time_it=True)
+    ok &= run(4112, 1024, 4096, act=0, time_it=True)
+    ok &= run(20000, 768, 3072, act=2, time_it=True)
     print("GEMM_DEBUG", "PASS" if ok else "FAIL")
     sys.exit(0 if ok else 1)
