@@ -106,6 +106,7 @@ PROTOTYPES = {
     "b200_clip_set_profiling": (_i, [_vp, _i]),
     "b200_layernorm_bf16_device": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "b200_attention_bf16_device": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_attention_tc_bf16_device": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_gemm_set_pair_mode": (_i, [_i]),
     "b200_gemm_bf16_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

@@ -37,6 +37,11 @@ struct Tower {
   // activations
   __nv_bfloat16 *x = nullptr, *h = nullptr, *qkv = nullptr, *a = nullptr, *f = nullptr;
   CUtensorMap tm_h, tm_a, tm_f;
+  // tcgen05 attention (head dim 64, T <= 320): V^T buffer + maps over qkv / V^T
+  bool use_tc_attn = false;
+  int Tp = 0;
+  __nv_bfloat16* vt = nullptr;
+  CUtensorMap tm_qk, tm_vt;
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
   __nv_bfloat16* proj = nullptr;             // [width, D]
 };
@@ -124,6 +129,15 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
   B200_TRY(make_tmap_2d(&t->tm_h, t->h, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_a, t->a, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_f, t->f, 1, rows, c.mlp, c.mlp, GEMM_BM, GEMM_BK));
+  t->use_tc_attn = attention_tc_supported(T, c.heads, w);
+  if (t->use_tc_attn) {
+    t->Tp = (T + 7) / 8 * 8;
+    const size_t vt_rows = (size_t)m->cfg.max_batch * c.heads * 64;
+    B200_TRY(dev_alloc(m, &t->vt, vt_rows * t->Tp));
+    B200_CUDA(cudaMemset(t->vt, 0, vt_rows * t->Tp * 2));  // key padding stays zero (0 * garbage would be NaN)
+    B200_TRY(make_tmap_2d(&t->tm_qk, t->qkv, 1, rows, 3 * (size_t)w, 3 * (size_t)w, 128, 64));
+    B200_TRY(make_tmap_2d(&t->tm_vt, t->vt, 1, vt_rows, t->Tp, t->Tp, 64, 64));
+  }
   return B200_OK;
 }
 
@@ -163,9 +177,13 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln1_g, L.ln1_b, M, w, st)); }
     GemmEpilogue e1; e1.out = t.qkv; e1.out_ld = 3 * w;
+    if (t.use_tc_attn) {
+      e1.vt = t.vt; e1.vt_col0 = 2 * w; e1.vt_T = t.T; e1.vt_Tp = t.Tp; e1.vt_hd = 64; e1.vt_heads = t.heads;
+    }
     B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
-      B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
+      if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+      else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
     B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st));
     { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
@@ -458,6 +476,17 @@ int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int
   B200_CHECK(d_qkv && d_out && B >= 0 && T >= 1, B200_ERR_INVALID, "attention: bad argument");
   DeviceGuard g(device);
   return attention((const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, (cudaStream_t)stream);
+}
+
+int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads, int w,
+                                  int causal, int device, void* stream) {
+  B200_CHECK(d_qkv && d_vt && d_out && B >= 0 && T >= 1 && Tp >= T && Tp % 8 == 0, B200_ERR_INVALID,
+             "attention_tc: bad argument");
+  DeviceGuard g(device);
+  CUtensorMap tq, tv;
+  B200_TRY(make_tmap_2d(&tq, d_qkv, 1, (uint64_t)B * T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128, 64));
+  B200_TRY(make_tmap_2d(&tv, d_vt, 1, (uint64_t)B * heads * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 64));
+  return attention_tc(tq, tv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device), (cudaStream_t)stream);
 }
 
 int b200_clip_set_profiling(b200_clip* m, int on) {

@@ -104,6 +104,7 @@ int token_argmax(const int64_t* tokens, int* pool_idx, int B, int T, cudaStream_
 
 // ---- LayerNorm: one warp per row, the row lives in registers between the two passes -------------
 constexpr int LN_MAXC = 8;  // 16-byte chunks per lane: w <= 2048
+template <int CPL>          // chunks per lane actually present: ceil(w / 256)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloat16* __restrict__ out, int64_t out_ld,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int w) {
@@ -112,10 +113,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloa
   if (row >= rows) return;
   const int chunks = w >> 3;
   const __nv_bfloat16* src = in + row * in_ld;
-  float v[LN_MAXC][8];
+  float v[CPL][8];
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; c++) {
+  for (int c = 0; c < CPL; c++) {
     const int ci = c * 32 + lane;
     if (ci < chunks) {
       const uint4 u = *reinterpret_cast<const uint4*>(src + ci * 8);
@@ -134,7 +135,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloa
   const float mean = sum / (float)w;
   float ss = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; c++) {
+  for (int c = 0; c < CPL; c++) {
     if (c * 32 + lane < chunks) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -148,7 +149,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloa
   const float rstd = rsqrtf(ss / (float)w + 1e-5f);
   __nv_bfloat16* dst = out + row * out_ld;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; c++) {
+  for (int c = 0; c < CPL; c++) {
     const int ci = c * 32 + lane;
     if (ci < chunks) {
       const float4 g0 = *reinterpret_cast<const float4*>(gamma + ci * 8);
@@ -173,7 +174,17 @@ int layernorm_rows(const __nv_bfloat16* in, int64_t in_ld, __nv_bfloat16* out, i
                    const float* beta, int64_t rows, int w, cudaStream_t st) {
   B200_CHECK(w % 8 == 0 && w <= LN_MAXC * 256, B200_ERR_UNSUPPORTED, "layernorm: width %d (need %%8, <= 2048)", w);
   if (rows == 0) return B200_OK;
-  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  switch ((w / 8 + 31) / 32) {
+    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 6: layernorm_kernel<6><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    case 7: layernorm_kernel<7><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+    default: layernorm_kernel<8><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
+  }
   B200_LAUNCH_OK();
   return B200_OK;
 }

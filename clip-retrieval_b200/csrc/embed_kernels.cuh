@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the embed path (declarations; embed_kernels.cu, attention.cu).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace b200 {
 
@@ -18,6 +19,11 @@ int layernorm_rows(const __nv_bfloat16* in, int64_t in_ld, __nv_bfloat16* out, i
                    const float* beta, int64_t rows, int w, cudaStream_t st);
 // K4: multi-head attention over the fused qkv buffer [B*T, 3w] -> out [B*T, w]; causal for text.
 int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w, int causal, cudaStream_t st);
+// K4 on tcgen05 (attention_tc.cu): head dim 64, T <= 320.  tmQK: qkv buffer [rows, 3w] box 128x64;
+// tmVt: V^T buffer [B*heads*64, Tp] box 64x64 (written by the QKV GEMM epilogue, GemmEpilogue::vt).
+bool attention_tc_supported(int T, int heads, int w);
+int attention_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVt, __nv_bfloat16* out, int B, int T, int heads, int w,
+                 int causal, int sms, cudaStream_t st);
 // K8/K10/K11: pooled row (x[b*T + pool_index(b)]) -> LN -> @ proj [w, D] -> optional L2 normalise
 // -> fp16 or fp32.  pool_idx == nullptr pools token 0 (vision); else row pool_idx[b] (text EOT).
 int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx, const float* gamma, const float* beta,

@@ -37,7 +37,34 @@ struct GemmEpilogue {
   int64_t out_ld = 0;
   int out_group = 0;                        // > 0: out row = (row / g) * (g + 1) + 1 + row % g  (cls slot)
   int act = ACT_NONE;
+  // Optional transposed store of the V third of a QKV projection (columns >= vt_col0): element
+  // (row = b*T + t, col = vt_col0 + h*hd + dd) goes to vt[((b*heads + h)*hd + dd) * vt_Tp + t], i.e. V^T
+  // per (sample, head) with keys contiguous — the K-major B operand of the P.V MMA (attention_tc.cu).
+  __nv_bfloat16* vt = nullptr;
+  int vt_col0 = 0, vt_T = 1, vt_Tp = 0, vt_hd = 64, vt_heads = 1;
 };
+
+// Per-row constants of the epilogue, computed once per tile.
+struct EpiRow {
+  __nv_bfloat16* out_ptr;
+  const __nv_bfloat16* res_ptr;
+  __nv_bfloat16* vt_ptr;   // vt + (b*heads*hd) * Tp + t   (add (h*hd + dd) * Tp)
+};
+__device__ __forceinline__ EpiRow epi_row(const GemmEpilogue& ep, int row, int n0) {
+  EpiRow r;
+  int64_t out_row = row;
+  if (ep.out_group > 0) out_row = (int64_t)(row / ep.out_group) * (ep.out_group + 1) + 1 + row % ep.out_group;
+  int64_t res_row = row;
+  if (ep.res_row_mod > 0) res_row = ep.res_row_off + row % ep.res_row_mod;
+  r.out_ptr = ep.out + out_row * ep.out_ld + n0;
+  r.res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
+  r.vt_ptr = nullptr;
+  if (ep.vt) {
+    const int b = row / ep.vt_T, t = row - b * ep.vt_T;
+    r.vt_ptr = ep.vt + (int64_t)b * ep.vt_heads * ep.vt_hd * ep.vt_Tp + t;
+  }
+  return r;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -76,6 +103,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+// bias + activation + residual + bf16 store of 8 consecutive columns (col = offset inside the tile)
+__device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r8,
+                                           const float* s_bias, int col, int n0) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+  if (er.res_ptr) {
+    const uint4 rr = *reinterpret_cast<const uint4*>(er.res_ptr + col);
+    const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z), dd = unpack_bf16x2(rr.w);
+    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+    v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+  }
+  if (er.vt_ptr != nullptr && n0 + col >= ep.vt_col0) {
+    __nv_bfloat16* p = er.vt_ptr + (int64_t)(n0 + col - ep.vt_col0) * ep.vt_Tp;
+#pragma unroll
+    for (int j = 0; j < 8; j++) p[(int64_t)j * ep.vt_Tp] = __float2bfloat16_rn(v[j]);
+    return;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(er.out_ptr + col) = o;
 }
 
 template <int BN>
@@ -194,12 +247,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < M;
-      int64_t out_row = row;
-      if (ep.out_group > 0) out_row = (int64_t)(row / ep.out_group) * (ep.out_group + 1) + 1 + row % ep.out_group;
-      int64_t res_row = row;
-      if (ep.res_row_mod > 0) res_row = ep.res_row_off + row % ep.res_row_mod;
-      __nv_bfloat16* out_ptr = ep.out + out_row * ep.out_ld + n0;
-      const __nv_bfloat16* res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
+      const EpiRow er = epi_row(ep, row, n0);
 
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
@@ -216,24 +264,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             const int col = c * 32 + g * 8;
-            if (n0 + col < N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r[g * 8 + j]) + s_bias[col + j], ep.act);
-              if (res_ptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr + col);
-                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z),
-                             dd = unpack_bf16x2(rr.w);
-                v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-                v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(out_ptr + col) = o;
-            }
+            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0);
           }
         }
       }

@@ -54,7 +54,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < G2_STAGES; s++) {
-        ptx::mbar_init(&full[s], 2);   // one arrive per CTA's producer (used in the leader only)
+        ptx::mbar_init(&full[s], 1);   // the leader's producer arrives; both CTAs' TMA bytes are credited here
         ptx::mbar_init(&empty[s], 1);  // multicast commit from the leader's MMA
       }
       for (int a = 0; a < 2; a++) {
@@ -77,7 +77,6 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t full0_remote = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
       for (int tile = pair; tile < tiles; tile += npairs) {
         int m_blk, n_blk;
         gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
@@ -87,8 +86,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                                 m_blk * G2_BM + (int)rank * 128);
           ptx::tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, &full[stage], kbi * GEMM_BK,
                                 n_blk * G2_BN + (int)rank * 128);
+          // The peer's loads complete on the leader's barrier too (peer bit cleared in the TMA); the peer
+          // cannot run a ring cycle ahead because its empty[] is released by the leader's MMA commit.
           if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
-          else ptx::mbar_arrive_cluster(full0_remote + (uint32_t)stage * 8u);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -144,12 +144,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 
       const int row = m_blk * G2_BM + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = row < M;
-      int64_t out_row = row;
-      if (ep.out_group > 0) out_row = (int64_t)(row / ep.out_group) * (ep.out_group + 1) + 1 + row % ep.out_group;
-      int64_t res_row = row;
-      if (ep.res_row_mod > 0) res_row = ep.res_row_off + row % ep.res_row_mod;
-      __nv_bfloat16* out_ptr = ep.out + out_row * ep.out_ld + n0;
-      const __nv_bfloat16* res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
+      const EpiRow er = epi_row(ep, row, n0);
 
 #pragma unroll 1
       for (int c = 0; c < G2_BN / 32; c++) {
@@ -168,24 +163,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             const int col = c * 32 + g * 8;
-            if (n0 + col < N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r[g * 8 + j]) + s_bias[col + j], ep.act);
-              if (res_ptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr + col);
-                const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z),
-                             dd = unpack_bf16x2(rr.w);
-                v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-                v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(out_ptr + col) = o;
-            }
+            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0);
           }
         }
       }

@@ -13,6 +13,7 @@ struct b200_index {
   bool reserved = false;
   __half* rows = nullptr;   // flat: insertion order.  IVF: list order after finalize.
   int64_t id_base = 0;
+  bool use_staged = true;   // FMA scan through the cp.async.bulk shared-memory ring (knn_scan.cu)
   bool use_mma = true;      // batched queries go through the tcgen05 scan (knn_mma.cu)
 
   // IVF-Flat

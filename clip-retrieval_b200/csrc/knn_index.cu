@@ -308,7 +308,8 @@ int b200_index_get_nprobe(const b200_index* idx) { return idx ? idx->nprobe : -1
 
 int b200_index_set_tensor_scan(b200_index* idx, int on) {
   B200_CHECK(idx, B200_ERR_INVALID, "set_tensor_scan: null index");
-  idx->use_mma = on != 0;
+  idx->use_mma = (on & 1) != 0;
+  idx->use_staged = (on & 4) == 0;  // bit 2 set: also disable the cp.async.bulk ring (A/B)
   return B200_OK;
 }
 

@@ -35,12 +35,12 @@ constexpr int MS_BM = 128;       // rows per tile
 constexpr int MS_QG = 128;       // queries per group (256 MMA columns: hi | lo)
 constexpr int MS_BN = 256;
 constexpr int MS_BK = 64;
-constexpr int MS_STAGES = 4;
+constexpr int MS_STAGES = 6;
 constexpr int MS_CAP = 256;      // candidate buffer entries per (CTA, query)
 constexpr int MS_KMAX = 128;     // k supported by this path (CAP - BM)
 constexpr int MS_THREADS = 192;
 constexpr int MS_A_BYTES = MS_BM * MS_BK * 2;
-constexpr int MS_B_BYTES = MS_BN * MS_BK * 2;
+constexpr int MS_B_BYTES = (MS_BN / 2) * MS_BK * 2;  // each CTA of the pair stages half of the Q' tile
 constexpr int MS_STAGE_BYTES = MS_A_BYTES + MS_B_BYTES;
 
 // fp32 queries -> fp16 [groups*256, d]: row g*256 + c (c < 128) = hi of query g*128 + c,
@@ -96,7 +96,7 @@ __device__ __forceinline__ float compact_buffer(unsigned long long* buf, int cou
   return last != 0ull ? key_score(last) : -INFINITY;
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MS_THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n, int d,
                 int nq, int groups, int k, unsigned long long* __restrict__ cand /* [grid][groups*128][CAP] */,
                 unsigned long long* __restrict__ dense /* [nq][grid][k] */) {
@@ -114,7 +114,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row_tiles = (n + MS_BM - 1) / MS_BM;
+  // CTA pair (cta_group::2): a pair owns 256-row tiles, each CTA stages its own 128 rows of X and half
+  // of the 256 Q' rows (CTA 0 the hi parts, CTA 1 the lo parts); the epilogue is per CTA (its rows).
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int64_t row_tiles = (n + 2 * MS_BM - 1) / (2 * MS_BM);
   const int kb = (d + MS_BK - 1) / MS_BK;
 
   for (int i = threadIdx.x; i < groups * MS_QG; i += blockDim.x) {
@@ -133,16 +138,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       for (int a = 0; a < 2; a++) {
         ptx::mbar_init(&tfull[a], 1);
-        ptx::mbar_init(&tempty[a], 4);
+        ptx::mbar_init(&tempty[a], 8);
       }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(s_tmem, 512);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_pair(s_tmem, 512);
+    ptx::tmem_relinquish_pair();
   }
-  ptx::tc_fence_before();
   __syncthreads();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -150,13 +156,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+      for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
         for (int g = 0; g < groups; g++) {
           for (int kbi = 0; kbi < kb; kbi++) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full[stage], MS_STAGE_BYTES);
-            ptx::tma_load_2d(sA + stage * MS_A_BYTES, &tmX, &full[stage], kbi * MS_BK, (int32_t)(rt * MS_BM));
-            ptx::tma_load_2d(sB + stage * MS_B_BYTES, &tmQ, &full[stage], kbi * MS_BK, g * MS_BN);
+            ptx::tma_load_2d_pair(sA + stage * MS_A_BYTES, &tmX, &full[stage], kbi * MS_BK,
+                                  (int32_t)(rt * 2 * MS_BM + rank * MS_BM));
+            ptx::tma_load_2d_pair(sB + stage * MS_B_BYTES, &tmQ, &full[stage], kbi * MS_BK,
+                                  g * MS_BN + (int)rank * (MS_BN / 2));
+            if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * MS_STAGE_BYTES);
             if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -164,13 +172,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(MS_BM, MS_BN, false);
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(2 * MS_BM, MS_BN, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+      for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
         for (int g = 0; g < groups; g++) {
           ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
@@ -182,11 +190,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + stage * MS_B_BYTES));
 #pragma unroll
             for (int kk = 0; kk < MS_BK / 16; kk++)
-              ptx::umma_f16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kbi | kk) != 0 ? 1u : 0u);
-            ptx::umma_commit(&empty[stage]);
+              ptx::umma_f16_pair(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kbi | kk) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(&empty[stage], 3);
             if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&tfull[acc]);
+          ptx::umma_commit_pair(&tfull[acc], 3);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -200,32 +208,58 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     unsigned long long* my_cand = cand + (int64_t)blockIdx.x * groups * MS_QG * MS_CAP;
-    for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
-      const int64_t row = rt * MS_BM + q4 * 32 + lane;
+    const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
+    for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
+      const int64_t row = rt * 2 * MS_BM + rank * MS_BM + q4 * 32 + lane;
       const bool row_ok = row < n;
       for (int g = 0; g < groups; g++) {
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tbase = tmem_base + acc * MS_BN + ((uint32_t)(q4 * 32) << 16);
+        const int gq = min(MS_QG, nq - g * MS_QG);   // live queries of this group
+        const int nchunks = (gq + 31) / 32;
 #pragma unroll 1
-        for (int c = 0; c < MS_QG / 32; c++) {
+        for (int c = 0; c < nchunks; c++) {
           uint32_t hi[32], lo[32];
           ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
           ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
           ptx::tmem_ld_wait();
-          if (c == MS_QG / 32 - 1) {
+          if (c == nchunks - 1) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&tempty[acc]);
+              else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
+            }
           }
           if (row_ok) {
+            // branch-free common case: recombine, compare against the 32 thresholds (vector loads from
+            // shared memory), collect the rare hits in a bit mask; only then take the append path.
+            const int qbase = g * MS_QG + c * 32;
+            const float4* thr4 = reinterpret_cast<const float4*>(s_thr + qbase);
+            uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int q = g * MS_QG + c * 32 + j;
-              const float s = fmaf(__uint_as_float(lo[j]), 1.0f / 2048.0f, __uint_as_float(hi[j]));
-              if (s >= s_thr[q] && q < nq) {
-                const int pos = atomicAdd(&s_cnt[q], 1);
-                if (pos < MS_CAP) my_cand[(int64_t)q * MS_CAP + pos] = make_key(s, (uint32_t)row);
+            for (int j4 = 0; j4 < 8; j4++) {
+              const float4 t = thr4[j4];
+              const float th[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const int j = j4 * 4 + e;
+                const float s = fmaf(__uint_as_float(lo[j]), 1.0f / 2048.0f, __uint_as_float(hi[j]));
+                hi[j] = __float_as_uint(s);
+                mask |= (s >= th[e]) ? (1u << j) : 0u;
+              }
+            }
+            const int live = nq - qbase;  // queries of this chunk that exist
+            if (live < 32) mask &= (1u << (live > 0 ? live : 0)) - 1u;
+            if (mask) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                if (mask & (1u << j)) {
+                  const int q = qbase + j;
+                  const int pos = atomicAdd(&s_cnt[q], 1);
+                  if (pos < MS_CAP) my_cand[(int64_t)q * MS_CAP + pos] = make_key(__uint_as_float(hi[j]), (uint32_t)row);
+                }
               }
             }
           }
@@ -235,7 +269,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // compaction of this group's buffers that could overflow during the next tile
         __threadfence_block();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int qq = ew; qq < MS_QG; qq += 4) {
+        for (int qq = ew; qq < gq; qq += 4) {
           const int q = g * MS_QG + qq;
           const int cnt = s_cnt[q];
           if (cnt > MS_CAP - MS_BM) {
@@ -260,8 +294,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t rows, uint64_t cols, uint64_t ld_elems,
@@ -273,7 +307,7 @@ int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const flo
   const int d = idx->d;
   B200_CHECK(k <= MS_KMAX, B200_ERR_UNSUPPORTED, "mma scan: k=%d > %d", k, MS_KMAX);
   B200_CHECK(n < (1ll << 31), B200_ERR_UNSUPPORTED, "mma scan: at most 2^31 rows per shard");
-  const int grid = idx->sms;
+  const int grid = idx->sms & ~1;  // CTA pairs
   const int QMAX = 1024;  // queries per launch (thresholds/counters live in shared memory)
   for (int q0 = 0; q0 < nq; q0 += QMAX) {
     const int nqb = std::min(QMAX, nq - q0);
@@ -294,7 +328,7 @@ int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const flo
     }
     CUtensorMap tmX, tmQ;
     B200_TRY(make_tmap_2d(&tmX, rows, 0, (uint64_t)n, (uint64_t)d, (uint64_t)d, MS_BM, MS_BK));
-    B200_TRY(make_tmap_2d(&tmQ, Qp, 0, (uint64_t)groups * MS_BN, (uint64_t)d, (uint64_t)d, MS_BN, MS_BK));
+    B200_TRY(make_tmap_2d(&tmQ, Qp, 0, (uint64_t)groups * MS_BN, (uint64_t)d, (uint64_t)d, MS_BN / 2, MS_BK));
     const size_t smem = (size_t)MS_STAGES * MS_STAGE_BYTES + (size_t)groups * MS_QG * 8 + 256 + 1024;
     B200_CUDA(cudaFuncSetAttribute(scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if ((int)idx->ev.size() < idx->ev_used + 2) {

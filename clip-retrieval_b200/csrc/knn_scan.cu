@@ -121,6 +121,178 @@ flat_scan_kernel(const uint4* __restrict__ X, int64_t n, int cpr, const float* _
   }
 }
 
+// ---- staged variant: cp.async.bulk ring -------------------------------------------------------------
+// Same arithmetic and the same per-warp candidate lists, but the rows reach the SM through a
+// shared-memory ring filled by 1-D bulk async copies (one elected producer thread, one mbarrier
+// per slot), so the bytes in flight per SM (STAGES x 32 rows x 2d bytes, ~190 KB) no longer depend
+// on how many loads the register file can hold.  One CTA per SM: 8 consumer warps + 1 producer.
+constexpr int TS_ROWS = 32;       // rows per slot (4 per consumer warp)
+constexpr int TS_CONSUMERS = 8;   // consumer warps
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void ts_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int NQ, int CH>
+__global__ void __launch_bounds__((TS_CONSUMERS + 1) * 32, 1)
+flat_scan_staged_kernel(const uint4* __restrict__ X, int64_t n, int cpr, const float* __restrict__ Q, int nq_valid,
+                        int k, int stages, unsigned long long* __restrict__ out_keys, int64_t out_stride_q) {
+  extern __shared__ __align__(128) unsigned char ts_smem[];
+  const int row_bytes = cpr * 16;
+  const int slot_bytes = TS_ROWS * row_bytes;
+  unsigned char* ring = ts_smem;                                                          // [stages][slot_bytes]
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(ts_smem + (size_t)stages * slot_bytes);  // [8][NQ][k]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_keys + (size_t)TS_CONSUMERS * NQ * k);
+  uint64_t* empty = full + stages;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) {
+      ts_mbar_init(&full[s], 1);
+      ts_mbar_init(&empty[s], TS_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t nblocks = (n + TS_ROWS - 1) / TS_ROWS;
+
+  if (warp == TS_CONSUMERS) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        ts_mbar_wait(&empty[s], phase ^ 1);
+        const int64_t r0 = b * TS_ROWS;
+        const int rows = (int)((n - r0) < TS_ROWS ? (n - r0) : TS_ROWS);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)row_bytes;
+        ts_mbar_expect(&full[s], bytes);
+        bulk_copy_g2s(ring + (size_t)s * slot_bytes, X + r0 * cpr, bytes, &full[s]);
+        if (++s == stages) { s = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  unsigned long long* wkeys = s_keys + (size_t)warp * NQ * k;
+  for (int i = lane; i < NQ * k; i += 32) wkeys[i] = 0ull;
+  __syncwarp();
+  float qr[NQ][CH][8];
+  const int d = cpr * 8;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+      const int ci = c * 32 + lane;
+      if (q < nq_valid && ci < cpr) {
+        const float4 a = *reinterpret_cast<const float4*>(Q + (size_t)q * d + ci * 8);
+        const float4 b = *reinterpret_cast<const float4*>(Q + (size_t)q * d + ci * 8 + 4);
+        qr[q][c][0] = a.x; qr[q][c][1] = a.y; qr[q][c][2] = a.z; qr[q][c][3] = a.w;
+        qr[q][c][4] = b.x; qr[q][c][5] = b.y; qr[q][c][6] = b.z; qr[q][c][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) qr[q][c][j] = 0.0f;
+      }
+    }
+  }
+  unsigned long long worst[NQ];
+  int worst_pos[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) { worst[q] = 0ull; worst_pos[q] = 0; }
+  constexpr int V = SCAN_U * NQ;
+  constexpr int SH = 5 - Log2<V>::v;
+
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    ts_mbar_wait(&full[s], phase);
+    const uint4* slot = reinterpret_cast<const uint4*>(ring + (size_t)s * slot_bytes);
+    const int64_t r0 = b * TS_ROWS + warp * SCAN_U;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; i++) acc[i] = 0.0f;
+#pragma unroll
+    for (int u = 0; u < SCAN_U; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int ci = c * 32 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + u < n && ci < cpr) v = slot[(warp * SCAN_U + u) * cpr + ci];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 t = __half22float2(h2[j]);
+          f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[u * NQ + q] = fmaf(f[j], qr[q][c][j], acc[u * NQ + q]);
+        }
+      }
+    }
+    // the slot's bytes are in registers: hand it back to the producer before the reduction
+    __syncwarp();
+    if (lane == 0) ts_mbar_arrive(&empty[s]);
+    if (++s == stages) { s = 0; phase ^= 1; }
+
+    warp_transpose_reduce<V>(acc, lane);
+    const float sc = acc[0];
+    const int vi = lane >> SH;
+    const int my_q = vi % NQ;
+    const int64_t my_r = r0 + vi / NQ;
+    unsigned long long wq = worst[0];
+#pragma unroll
+    for (int q = 1; q < NQ; q++) if (my_q == q) wq = worst[q];
+    const unsigned long long key = make_key(sc, (uint32_t)my_r);
+    const bool live = ((lane & ((1 << SH) - 1)) == 0) && my_r < n && my_q < nq_valid && (sc == sc);
+    unsigned pend = __ballot_sync(FULL, live && key > wq);
+    while (pend) {
+      const int src = __ffs(pend) - 1;
+      pend &= pend - 1;
+      const unsigned long long ckey = __shfl_sync(FULL, key, src);
+      const int cq = (src >> SH) % NQ;
+#pragma unroll
+      for (int q = 0; q < NQ; q++)
+        if (cq == q) warp_list_insert(wkeys + q * k, k, ckey, worst[q], worst_pos[q], lane);
+    }
+  }
+  __syncwarp();
+  const int64_t gw = (int64_t)blockIdx.x * TS_CONSUMERS + warp;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    if (q < nq_valid) {
+      unsigned long long* o = out_keys + (int64_t)q * out_stride_q + gw * k;
+      for (int j = lane; j < k; j += 32) o[j] = wkeys[q * k + j];
+    }
+  }
+}
+
 // Select the k best of M candidate keys per query: grid (slices, nq); every block streams its
 // slice through a C-entry shared buffer, keeping a sorted top-k at the front.
 __global__ void __launch_bounds__(1024)
@@ -217,6 +389,25 @@ static scan_fn pick_scan(int nqp, int ch) {
   return pick_ch<1>(ch);
 }
 
+typedef void (*staged_fn)(const uint4*, int64_t, int, const float*, int, int, int, unsigned long long*, int64_t);
+template <int NQ>
+static staged_fn pick_staged_ch(int ch) {
+  switch (ch) {
+    case 1: return flat_scan_staged_kernel<NQ, 1>;
+    case 2: return flat_scan_staged_kernel<NQ, 2>;
+    case 3: return flat_scan_staged_kernel<NQ, 3>;
+  }
+  if constexpr (NQ <= 2) {
+    if (ch == 4) return flat_scan_staged_kernel<NQ, 4>;
+  }
+  return nullptr;
+}
+static staged_fn pick_staged(int nqp, int ch) {
+  if (nqp == 4) return pick_staged_ch<4>(ch);
+  if (nqp == 2) return pick_staged_ch<2>(ch);
+  return pick_staged_ch<1>(ch);
+}
+
 struct ScanPlan {
   int nqp;       // queries per pass
   int threads;   // block size
@@ -224,6 +415,9 @@ struct ScanPlan {
   int C;         // select buffer entries
   size_t smem;
   scan_fn fn;
+  staged_fn sfn = nullptr;  // cp.async.bulk ring variant (preferred when it fits)
+  int stages = 0;
+  int warps_out = 0;        // candidate lists written per block
 };
 
 static int plan_scan(const b200_index* idx, int k, int nq, ScanPlan* p) {
@@ -256,6 +450,25 @@ static int plan_scan(const b200_index* idx, int k, int nq, ScanPlan* p) {
   p->nqp = nqp;
   p->threads = threads;
   p->grid = idx->sms * per_sm;
+  p->warps_out = threads / 32;
+  // staged variant: one block per SM, ring of 32-row slots in shared memory
+  if (idx->use_staged) {
+    const size_t slot = (size_t)TS_ROWS * idx->d * 2;
+    const size_t lists = (size_t)TS_CONSUMERS * nqp * k * 8;
+    const size_t fixed = lists + 256;
+    const size_t budget = 220 * 1024;
+    staged_fn sf = pick_staged(nqp, ch);
+    if (sf && fixed + 3 * slot <= budget) {
+      int stages = (int)std::min<size_t>(8, (budget - fixed) / slot);
+      p->sfn = sf;
+      p->stages = stages;
+      p->smem = (size_t)stages * slot + fixed;
+      p->threads = (TS_CONSUMERS + 1) * 32;
+      p->grid = idx->sms;
+      p->warps_out = TS_CONSUMERS;
+      B200_CUDA(cudaFuncSetAttribute((const void*)sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    }
+  }
   return B200_OK;
 }
 
@@ -270,7 +483,7 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
     return scan_topk_keys_mma(idx, rows, n, d_q, nq, k, d_keys_out, st);
   ScanPlan p;
   B200_TRY(plan_scan(idx, k, nq, &p));
-  const int64_t total_warps = (int64_t)p.grid * (p.threads / 32);
+  const int64_t total_warps = (int64_t)p.grid * p.warps_out;
   const int64_t M1 = total_warps * k;
   int slices = (int)std::min<int64_t>(64, std::max<int64_t>(1, M1 / (4 * (int64_t)(p.C - k))));
   const int QB = 64;  // queries per batch (bounds the scratch)
@@ -298,7 +511,10 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
       const int valid = std::min(p.nqp, qb - qq);
       const float* qptr = d_q + (size_t)(q0 + qq) * d;
       unsigned long long* kp = k1 + (size_t)qq * M1;
-      p.fn<<<p.grid, p.threads, p.smem, st>>>(reinterpret_cast<const uint4*>(rows), n, d / 8, qptr, valid, k, kp, M1);
+      if (p.sfn)
+        p.sfn<<<p.grid, p.threads, p.smem, st>>>(reinterpret_cast<const uint4*>(rows), n, d / 8, qptr, valid, k, p.stages, kp, M1);
+      else
+        p.fn<<<p.grid, p.threads, p.smem, st>>>(reinterpret_cast<const uint4*>(rows), n, d / 8, qptr, valid, k, kp, M1);
       B200_LAUNCH_OK();
       idx->last_scan_launches++;
     }

@@ -198,6 +198,10 @@ int b200_layernorm_bf16_device(const void* d_in, void* d_out, const float* d_gam
                                int64_t rows, int w, int device, void* stream);
 int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int heads, int w, int causal,
                                int device, void* stream);
+/* tcgen05 attention (head dim 64, T <= 320): the Q and K thirds are read from d_qkv, V^T from d_vt
+ * ([B*heads*64, Tp] bf16, keys contiguous, columns >= T zero) — the layout the QKV GEMM epilogue writes. */
+int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads,
+                                  int w, int causal, int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -162,3 +162,33 @@ def test_zero_feature_row_is_nan_like_reference():
     model.load_state_dict(sd)
     out = model.embed_image(clip_ref.synth_images(2, cfg))
     assert np.isnan(out.astype(np.float32)).all()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,T,heads,causal", [(2, 257, 16, 0), (3, 77, 8, 1), (2, 50, 12, 0), (1, 1, 2, 0), (5, 128, 4, 1),
+                                              (1, 320, 2, 0), (40, 257, 16, 0)])
+def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
+    """tcgen05 attention (TMA K / V^T tiles, scores and output in TMEM, P through swizzled shared
+    memory) against a plain fp32 PyTorch softmax(QK^T)V of the same bf16 inputs."""
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    hd = 64
+    w = heads * hd
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + w)
+    qkv = torch.randn(B * T, 3 * w, device="cuda", generator=g).bfloat16()
+    Tp = (T + 7) // 8 * 8
+    v = qkv[:, 2 * w:].view(B, T, heads, hd)
+    vt = torch.zeros(B, heads, hd, Tp, device="cuda", dtype=torch.bfloat16)
+    vt[..., :T] = v.permute(0, 2, 3, 1)
+    out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), vt.data_ptr(), Tp, out.data_ptr(), B, T, heads, w, causal, 0,
+                                            torch.cuda.current_stream().cuda_stream), "attention_tc")
+    q, k, vv = qkv.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), device="cuda").triu_(1)
+    ref = (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(B * T, w)
+    err = (out.float() - ref).abs()
+    assert not torch.isnan(out.float()).any()
+    assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), "max err %g" % err.max().item()
