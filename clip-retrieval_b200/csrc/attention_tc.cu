@@ -21,15 +21,16 @@ constexpr int AT_HD = 64;
 constexpr int AT_MAXKEYS = 320;                 // 5 key blocks of 64
 constexpr int AT_Q_BYTES = 128 * AT_HD * 2;     // 16 KB
 constexpr int AT_K_BYTES = 3 * 128 * AT_HD * 2; // up to 384 key rows
-constexpr int AT_VT_BYTES = 5 * AT_HD * 64 * 2; // 5 boxes of [64 d x 64 keys]
+constexpr int AT_VT_BYTES = 3 * 128 * AT_HD * 2; // V as 3 boxes of [128 keys x 64 d] (or V^T: 5 boxes of [64 d x 64 keys])
 constexpr int AT_P_BYTES = 5 * 128 * 64 * 2;    // 5 key blocks of [128 rows x 64 keys]
-constexpr int AT_SMEM = 2 * AT_Q_BYTES + AT_K_BYTES + AT_VT_BYTES + AT_P_BYTES + 256 + 1024;
-constexpr int AT_THREADS = 192;
+constexpr int AT_SMEM = 2 * AT_Q_BYTES + AT_K_BYTES + AT_VT_BYTES + AT_P_BYTES + 2048 + 256 + 1024;
+constexpr int AT_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per SM sub-partition)
 constexpr int AT_O_COL = 320;
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt,
-                    __nv_bfloat16* __restrict__ out, int B, int T, int heads, int w, float scale_log2e, int causal) {
+                    __nv_bfloat16* __restrict__ out, int B, int T, int heads, int w, float scale_log2e, int causal,
+                    int v_direct) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -37,7 +38,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   uint8_t* sK = sQ + 2 * AT_Q_BYTES;        // [<=384 rows][128 B]
   uint8_t* sVt = sK + AT_K_BYTES;           // [5][64 rows][128 B]
   uint8_t* sP = sVt + AT_VT_BYTES;          // [5][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  float* s_xm = reinterpret_cast<float*>(sP + AT_P_BYTES);   // [2][128] partial row maxima of the two column halves
+  float* s_xl = s_xm + 256;                                  // [2][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xl + 256);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_free = bars + 1;
   uint64_t* q_full = bars + 2;    // [2]
@@ -70,9 +73,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         ptx::mbar_init(&q_empty[i], 1);
       }
       ptx::mbar_init(s_full, 1);
-      ptx::mbar_init(p_full, 4);
+      ptx::mbar_init(p_full, 8);
       ptx::mbar_init(o_full, 1);
-      ptx::mbar_init(o_empty, 4);
+      ptx::mbar_init(o_empty, 8);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -91,11 +94,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
         const int b = item / heads, h = item - b * heads;
         ptx::mbar_wait(kv_free, (it & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(kv_full, (uint32_t)(k_boxes * 128 * 128 + v_boxes * 64 * 128));
+        ptx::mbar_arrive_expect_tx(kv_full, (uint32_t)(k_boxes * 128 * 128 + (v_direct ? k_boxes * 128 * 128 : v_boxes * 64 * 128)));
         for (int i = 0; i < k_boxes; i++)
           ptx::tma_load_2d(sK + i * 128 * 128, &tmQK, kv_full, w + h * AT_HD, b * T + i * 128);
-        for (int i = 0; i < v_boxes; i++)
-          ptx::tma_load_2d(sVt + i * 64 * 128, &tmVt, kv_full, i * 64, (b * heads + h) * AT_HD);
+        if (v_direct) {
+          // V rows straight from the fused qkv buffer: [keys x 64 d], d contiguous = MN-major B operand
+          for (int i = 0; i < k_boxes; i++)
+            ptx::tma_load_2d(sVt + i * 128 * 128, &tmQK, kv_full, 2 * w + h * AT_HD, b * T + i * 128);
+        } else {
+          for (int i = 0; i < v_boxes; i++)
+            ptx::tma_load_2d(sVt + i * 64 * 128, &tmVt, kv_full, i * 64, (b * heads + h) * AT_HD);
+        }
         for (int mt = 0; mt < q_tiles; mt++, tc++) {
           const int buf = tc & 1;
           ptx::mbar_wait(&q_empty[buf], ((tc >> 1) & 1) ^ 1);
@@ -110,7 +119,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     if (lane == 0) {
       const uint32_t idesc_s1 = ptx::umma_idesc_f16(128, n1, true);
       const uint32_t idesc_s2 = ptx::umma_idesc_f16(128, n2 > 0 ? n2 : 16, true);
-      const uint32_t idesc_o = ptx::umma_idesc_f16(128, AT_HD, true);
+      // P.V: B = V^T tile, K-major (keys contiguous), or V itself as an MN-major operand (bit 16 of the
+      // instruction descriptor): rows of 64 d = 128 bytes, 8-key swizzle atoms 1024 bytes apart.
+      const uint32_t idesc_o = ptx::umma_idesc_f16(128, AT_HD, true) | (v_direct ? (1u << 16) : 0u);
       uint32_t it = 0, tc = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
         ptx::mbar_wait(kv_full, it & 1);
@@ -136,7 +147,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
           ptx::tc_fence_after();
           for (int ks = 0; ks < keys_pad / 16; ks++) {
             const uint64_t dp = ptx::umma_desc_k_sw128(ptx::smem_u32(sP + (ks >> 2) * (128 * 128))) + (uint64_t)((ks & 3) * 2);
-            const uint64_t dv = ptx::umma_desc_k_sw128(ptx::smem_u32(sVt + (ks >> 2) * (64 * 128))) + (uint64_t)((ks & 3) * 2);
+            const uint64_t dv = v_direct
+                ? ptx::umma_desc_k_sw128(ptx::smem_u32(sVt + ks * 16 * 128))     // 16 keys = 2 atoms of 8 rows
+                : ptx::umma_desc_k_sw128(ptx::smem_u32(sVt + (ks >> 2) * (64 * 128))) + (uint64_t)((ks & 3) * 2);
             ptx::umma_f16(tmem_base + AT_O_COL, dp, dv, idesc_o, ks != 0 ? 1u : 0u);
           }
           ptx::umma_commit(o_full);
@@ -146,11 +159,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     }
     __syncwarp();
   } else {
-    // ---------------- softmax + output (warps 2..5; thread = query row of the tile) ----------------
+    // ---------------- softmax + output (warps 2..9) ----------------
+    // thread = query row of the tile; the two warps that share a TMEM lane quarter split the key
+    // columns in halves and exchange their partial row max / row sum through shared memory.
     const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q4 * 32 + lane;                  // row inside the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const int chunks = (keys_pad + 31) / 32;
+    const int c_mid = (chunks + 1) / 2;
+    const int c_beg = half ? c_mid : 0, c_end = half ? chunks : c_mid;
     uint32_t tc = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int b = item / heads, h = item - b * heads;
@@ -159,36 +177,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         const int kmax = causal ? (qrow < T ? qrow : T - 1) : T - 1;  // last visible key
         ptx::mbar_wait(s_full, tc & 1);
         ptx::tc_fence_after();
-        // pass 1: row maximum over the visible keys
+        // pass 1: row maximum over the visible keys (key <= kmax) of this warp's columns
         float m = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < chunks; c++) {
+        for (int c = c_beg; c < c_end; c++) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(lane_base + c * 32, v);
           ptx::tmem_ld_wait();
+          const int lim = kmax - c * 32;   // columns j <= lim are visible
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (c * 32 + j <= kmax) m = fmaxf(m, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
+            m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
+            m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
+            m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
+          }
+          m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         }
-        // pass 2: p = exp2((s - m) * scale*log2e), row sum, bf16 P into the swizzled K-major tile
-        float l = 0.f;
+        s_xm[half * 128 + r] = m;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        m = fmaxf(s_xm[r], s_xm[128 + r]);
+        // pass 2: p = 2^((s - m) * scale*log2e) (ex2.approx, arguments <= 0), row sum, bf16 P into the
+        // swizzled K-major tile
+        float l0 = 0.f, l1 = 0.f;
         const float mb = m * scale_log2e;
 #pragma unroll 1
-        for (int c = 0; c < chunks; c++) {
+        for (int c = c_beg; c < c_end; c++) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(lane_base + c * 32, v);
           ptx::tmem_ld_wait();
+          const int lim = kmax - c * 32;
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const int key = c * 32 + j;
-            const float p0 = key <= kmax ? exp2f(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)) : 0.f;
-            const float p1 = key + 1 <= kmax ? exp2f(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)) : 0.f;
-            // the row sum uses the bf16-rounded probabilities the MMA will see
-            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-            const float2 pr = __bfloat1622float2(pb);
-            l += pr.x + pr.y;
-            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
+            p0 = j <= lim ? p0 : 0.f;
+            p1 = j + 1 <= lim ? p1 : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
           }
           // 32 keys = 4 chunks of 16 bytes inside key block (c >> 1), chunk index ((c & 1) * 4 + i) ^ (r & 7)
           uint8_t* blk = sP + (c >> 1) * (128 * 128) + r * 128;
@@ -198,36 +228,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
             *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
           }
         }
+        s_xl[half * 128 + r] = l0 + l1;
         ptx::fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core
         ptx::tc_fence_before();
-        __syncwarp();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         if (lane == 0) ptx::mbar_arrive(p_full);
-        // output
+        const float l = s_xl[r] + s_xl[128 + r];
+        // output: each half normalises and stores 32 of the 64 head columns
         ptx::mbar_wait(o_full, tc & 1);
         ptx::tc_fence_after();
-        uint32_t o0[32], o1[32];
-        ptx::tmem_ld_32x32b_x32(lane_base + AT_O_COL, o0);
-        ptx::tmem_ld_32x32b_x32(lane_base + AT_O_COL + 32, o1);
+        uint32_t o0[32];
+        ptx::tmem_ld_32x32b_x32(lane_base + AT_O_COL + half * 32, o0);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(o_empty);
         if (qrow < T) {
           const float inv = 1.0f / l;
-          __nv_bfloat16* op = out + ((size_t)b * T + qrow) * w + (size_t)h * AT_HD;
+          __nv_bfloat16* op = out + ((size_t)b * T + qrow) * w + (size_t)h * AT_HD + half * 32;
 #pragma unroll
           for (int g = 0; g < 4; g++) {
-            uint4 a, c2;
+            uint4 a;
             a.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
             a.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
             a.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
             a.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
-            c2.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
-            c2.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
-            c2.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
-            c2.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
             *reinterpret_cast<uint4*>(op + g * 8) = a;
-            *reinterpret_cast<uint4*>(op + 32 + g * 8) = c2;
           }
         }
       }
@@ -245,7 +271,7 @@ bool attention_tc_supported(int T, int heads, int w) {
 
 // qkv: [B*T, 3w] (Q and K thirds are read); vt: [B*heads*64, Tp] (V^T, keys contiguous, zero padded).
 int attention_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVt, __nv_bfloat16* out, int B, int T, int heads, int w,
-                 int causal, int sms, cudaStream_t st) {
+                 int causal, int v_direct, int sms, cudaStream_t st) {
   B200_CHECK(attention_tc_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
   if (B == 0) return B200_OK;
@@ -259,7 +285,7 @@ int attention_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVt, __nv_bfloat16
   const float scale_log2e = (1.0f / sqrtf((float)AT_HD)) * 1.4426950408889634f;
   const int items = B * heads;
   const int grid = items < sms ? items : sms;
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQK, tmVt, out, B, T, heads, w, scale_log2e, causal);
+  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQK, tmVt, out, B, T, heads, w, scale_log2e, causal, v_direct);
   B200_LAUNCH_OK();
   return B200_OK;
 }

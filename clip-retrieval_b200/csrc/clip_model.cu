@@ -70,10 +70,13 @@ struct b200_clip {
   // staging for the host entry points
   void* stage_in = nullptr;
   void* stage_out = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;   // host entry: H2D of sub-batch i+1 overlaps compute of i
+  cudaEvent_t ev_in[4] = {}, ev_done[4] = {};
   std::vector<void*> allocs;
   std::mutex mu;
   // timing
   bool profiling = false;
+  bool attn_v_direct = true;   // P.V reads V from the qkv buffer as an MN-major operand (no V^T copy)
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
   int span_used = 0;
@@ -124,6 +127,8 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
   B200_TRY(dev_alloc(m, &t->x, rows * w));
   B200_TRY(dev_alloc(m, &t->h, rows * w));
   B200_TRY(dev_alloc(m, &t->qkv, rows * 3 * w));
+  // rows past the current batch are read (then multiplied by P = 0) by the attention's 128-row V boxes: keep them finite
+  B200_CUDA(cudaMemset(t->qkv, 0, rows * 3 * w * 2));
   B200_TRY(dev_alloc(m, &t->a, rows * w));
   B200_TRY(dev_alloc(m, &t->f, rows * c.mlp));
   B200_TRY(make_tmap_2d(&t->tm_h, t->h, 1, rows, w, w, GEMM_BM, GEMM_BK));
@@ -177,12 +182,12 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln1_g, L.ln1_b, M, w, st)); }
     GemmEpilogue e1; e1.out = t.qkv; e1.out_ld = 3 * w;
-    if (t.use_tc_attn) {
+    if (t.use_tc_attn && !m->attn_v_direct) {
       e1.vt = t.vt; e1.vt_col0 = 2 * w; e1.vt_T = t.T; e1.vt_Tp = t.Tp; e1.vt_hd = 64; e1.vt_heads = t.heads;
     }
     B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
-      if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+      if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
     B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st));
@@ -363,6 +368,10 @@ int b200_clip_destroy(b200_clip* m) {
   cudaDeviceSynchronize();
   for (void* p : m->allocs) cudaFree(p);
   for (auto& s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  if (m->s_copy) {
+    cudaStreamDestroy(m->s_copy); cudaStreamDestroy(m->s_comp);
+    for (int i = 0; i < 4; i++) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_done[i]); }
+  }
   delete m;
   return B200_OK;
 }
@@ -436,23 +445,50 @@ int b200_clip_encode_text_device(b200_clip* m, const int64_t* d_tokens, int B, v
   return encode_device(m, d_tokens, B, d_out, out_dtype, normalize, false, (cudaStream_t)stream);
 }
 
+// Host-buffer entry (the mapper call).  Images are pipelined in sub-batches: the H2D copy of
+// sub-batch i+1 (copy stream) overlaps the forward of sub-batch i (compute stream); the staging
+// buffer is a ring of max_batch / sub-batch slots guarded by events.
 static int encode_host(b200_clip* m, const void* h_in, int B, void* h_out, int out_dtype, int normalize, bool image) {
   B200_CHECK(m && (B == 0 || (h_in && h_out)) && B >= 0, B200_ERR_INVALID, "encode: bad argument");
   B200_CHECK(m->loaded, B200_ERR_STATE, "encode: weights not loaded");
   std::lock_guard<std::mutex> lock(m->mu);
   DeviceGuard g(m->device);
+  if (!m->s_copy) {
+    B200_CUDA(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) {
+      B200_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    }
+  }
   const int mb = m->cfg.max_batch;
   const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
   const size_t out_stride = (size_t)m->cfg.embed_dim * (out_dtype == B200_OUT_F16 ? 2 : 4);
+  const int slots = (image && mb >= 256) ? 4 : 1;
+  const int SB = mb / slots;
   int launches = 0;
+  long gi = 0;  // sub-batches issued so far (slot = gi % slots)
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int nb = std::min(mb, B - b0);
-    B200_CUDA(cudaMemcpyAsync(m->stage_in, (const char*)h_in + (size_t)b0 * in_stride, nb * in_stride, cudaMemcpyHostToDevice, 0));
-    B200_TRY(encode_device(m, m->stage_in, nb, m->stage_out, out_dtype, normalize, image, 0));
-    launches += m->last_launches;
-    B200_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, m->stage_out, nb * out_stride, cudaMemcpyDeviceToHost, 0));
+    if (b0 > 0) B200_CUDA(cudaStreamSynchronize(m->s_comp));  // stage_out is reused per chunk
+    for (int s0 = 0; s0 < nb; s0 += SB, gi++) {
+      const int ns = std::min(SB, nb - s0);
+      const int slot = (int)(gi % slots);
+      char* stage = (char*)m->stage_in + (size_t)slot * SB * in_stride;
+      if (gi >= slots) B200_CUDA(cudaStreamWaitEvent(m->s_copy, m->ev_done[slot], 0));
+      B200_CUDA(cudaMemcpyAsync(stage, (const char*)h_in + (size_t)(b0 + s0) * in_stride, ns * in_stride,
+                                cudaMemcpyHostToDevice, m->s_copy));
+      B200_CUDA(cudaEventRecord(m->ev_in[slot], m->s_copy));
+      B200_CUDA(cudaStreamWaitEvent(m->s_comp, m->ev_in[slot], 0));
+      B200_TRY(encode_device(m, stage, ns, (char*)m->stage_out + (size_t)s0 * out_stride, out_dtype, normalize, image,
+                             m->s_comp));
+      B200_CUDA(cudaEventRecord(m->ev_done[slot], m->s_comp));
+      launches += m->last_launches;
+    }
+    B200_CUDA(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, m->stage_out, nb * out_stride, cudaMemcpyDeviceToHost,
+                              m->s_comp));
   }
-  B200_CUDA(cudaStreamSynchronize(0));
+  B200_CUDA(cudaStreamSynchronize(m->s_comp));
   m->last_launches = launches;
   return B200_OK;
 }
@@ -480,13 +516,16 @@ int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int
 
 int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads, int w,
                                   int causal, int device, void* stream) {
-  B200_CHECK(d_qkv && d_vt && d_out && B >= 0 && T >= 1 && Tp >= T && Tp % 8 == 0, B200_ERR_INVALID,
+  B200_CHECK(d_qkv && d_out && B >= 0 && T >= 1 && (d_vt == nullptr || (Tp >= T && Tp % 8 == 0)), B200_ERR_INVALID,
              "attention_tc: bad argument");
   DeviceGuard g(device);
   CUtensorMap tq, tv;
   B200_TRY(make_tmap_2d(&tq, d_qkv, 1, (uint64_t)B * T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128, 64));
-  B200_TRY(make_tmap_2d(&tv, d_vt, 1, (uint64_t)B * heads * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 64));
-  return attention_tc(tq, tv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device), (cudaStream_t)stream);
+  if (d_vt) B200_TRY(make_tmap_2d(&tv, d_vt, 1, (uint64_t)B * heads * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 64));
+  else tv = tq;
+  // d_vt == NULL: V is read from the qkv buffer (MN-major operand); else from the V^T buffer
+  return attention_tc(tq, tv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, d_vt == nullptr ? 1 : 0, sm_count(device),
+                      (cudaStream_t)stream);
 }
 
 int b200_clip_set_profiling(b200_clip* m, int on) {

@@ -21,7 +21,7 @@ namespace b200 {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per SM sub-partition)
 constexpr int GEMM_GROUP_M = 16;
 
 enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU = 2 };
@@ -88,8 +88,10 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int mb, int nb, int& 
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == ACT_QUICK_GELU) {
-    // x * sigmoid(1.702 x)
-    return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    // x * sigmoid(1.702 x), sigmoid(y) = 0.5 * tanh(y / 2) + 0.5: one MUFU op per element
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    return x * fmaf(0.5f, t, 0.5f);
   } else if (act == ACT_GELU) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
   }
@@ -165,7 +167,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       for (int a = 0; a < 2; a++) {
         ptx::mbar_init(&tfull[a], 1);
-        ptx::mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+        ptx::mbar_init(&tempty[a], 8);  // one arrive per epilogue warp
       }
       ptx::fence_barrier_init();
     }
@@ -230,17 +232,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int et = (warp - 2) * 32 + lane;  // 0..127
+    const int et = (warp - 2) * 32 + lane;  // 0..255
+    const int half = (warp - 2) >> 2;        // which half of the tile columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
       const int n0 = n_blk * BN;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int j = et; j < BN; j += 128) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int j = et; j < BN; j += 256) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
@@ -250,11 +253,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const EpiRow er = epi_row(ep, row, n0);
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         ptx::tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c == (half + 1) * (BN / 64) - 1) {
           // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
           ptx::tc_fence_before();
           __syncwarp();

@@ -59,7 +59,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       }
       for (int a = 0; a < 2; a++) {
         ptx::mbar_init(&tfull[a], 1);
-        ptx::mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+        ptx::mbar_init(&tempty[a], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
       }
       ptx::fence_barrier_init();
     }
@@ -126,7 +126,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   } else {
     // ---------------- epilogue (warps 2..5 of both CTAs) ----------------
     const int q = warp & 3;
-    const int et = (warp - 2) * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;  // 0..255
+    const int half = (warp - 2) >> 2;        // which half of the tile columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
@@ -134,10 +135,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int m_blk, n_blk;
       gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
       const int n0 = n_blk * G2_BN;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int j = et; j < G2_BN; j += 128) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int j = et; j < G2_BN; j += 256) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
@@ -147,11 +148,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       const EpiRow er = epi_row(ep, row, n0);
 
 #pragma unroll 1
-      for (int c = 0; c < G2_BN / 32; c++) {
+      for (int c = half * (G2_BN / 64); c < (half + 1) * (G2_BN / 64); c++) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         ptx::tmem_ld_wait();
-        if (c == G2_BN / 32 - 1) {
+        if (c == (half + 1) * (G2_BN / 64) - 1) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {

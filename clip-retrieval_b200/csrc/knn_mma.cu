@@ -36,8 +36,8 @@ constexpr int MS_QG = 128;       // queries per group (256 MMA columns: hi | lo)
 constexpr int MS_BN = 256;
 constexpr int MS_BK = 64;
 constexpr int MS_STAGES = 6;
-constexpr int MS_CAP = 256;      // candidate buffer entries per (CTA, query)
-constexpr int MS_KMAX = 128;     // k supported by this path (CAP - BM)
+constexpr int MS_CAP = 512;      // candidate buffer entries per (CTA, query)
+constexpr int MS_KMAX = 128;     // k supported by this path
 constexpr int MS_THREADS = 192;
 constexpr int MS_A_BYTES = MS_BM * MS_BK * 2;
 constexpr int MS_B_BYTES = (MS_BN / 2) * MS_BK * 2;  // each CTA of the pair stages half of the Q' tile
@@ -58,42 +58,44 @@ __global__ void split_queries_kernel(const float* __restrict__ Q, int nq, int d,
   Qp[((int64_t)g * MS_BN + MS_QG + c) * d + j] = lo;
 }
 
-// Keep the k best of a (CTA, query) candidate buffer; returns the new threshold score.
-// One warp; up to MS_CAP keys live in registers (8 per lane).
+// Keep the k best of a (CTA, query) candidate buffer (unsorted, in place, buf[0..k)); returns the
+// new threshold score.  One warp, the keys live in registers (MS_CAP/32 per lane).  The k-th largest
+// key is found by a most-significant-bit-first radix select (one warp-wide popcount per bit), then
+// the survivors are packed with ballot prefix sums — no sorting, ~2.5k cycles instead of ~20k.
 __device__ __forceinline__ float compact_buffer(unsigned long long* buf, int count, int k, int lane) {
-  unsigned long long v[MS_CAP / 32];
+  constexpr int R = MS_CAP / 32;
+  unsigned long long v[R];
 #pragma unroll
-  for (int i = 0; i < MS_CAP / 32; i++) {
+  for (int i = 0; i < R; i++) {
     const int j = i * 32 + lane;
     v[i] = j < count ? buf[j] : 0ull;
   }
   __syncwarp();
-  unsigned long long last = 0ull;
-  for (int r = 0; r < k; r++) {
-    unsigned long long m = v[0];
-    int mi = 0;
+  if (count <= k) return -INFINITY;
+  // radix select: `prefix` = the bits of the k-th largest key decided so far
+  unsigned long long prefix = 0ull, decided = 0ull;
+  int need = k;  // rank still to locate among keys matching the prefix
+  for (int bit = 63; bit >= 0; bit--) {
+    const unsigned long long b = 1ull << bit;
+    int c = 0;
 #pragma unroll
-    for (int i = 1; i < MS_CAP / 32; i++)
-      if (v[i] > m) { m = v[i]; mi = i; }
-    unsigned long long wm = m;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const unsigned long long t = __shfl_xor_sync(FULL, wm, o);
-      wm = t > wm ? t : wm;
-    }
-    // keys are unique (ids differ) unless zero; the first lane holding the maximum retires it
-    const unsigned who = __ballot_sync(FULL, m == wm);
-    if (wm != 0ull && lane == __ffs(who) - 1) {
-#pragma unroll
-      for (int i = 0; i < MS_CAP / 32; i++)
-        if (i == mi) v[i] = 0ull;
-    }
-    if (lane == 0) buf[r] = wm;
-    last = wm;
+    for (int i = 0; i < R; i++) c += ((v[i] & decided) == prefix && (v[i] & b)) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c >= need) prefix |= b;   // the k-th largest has this bit set
+    else need -= c;               // skip the c keys above, continue among those with the bit clear
+    decided |= b;
   }
-  for (int j = k + lane; j < MS_CAP; j += 32) buf[j] = 0ull;
+  const unsigned long long kth = prefix;  // keys are unique, so exactly k keys are >= kth
+  int base = 0;
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const bool keep = v[i] >= kth && v[i] != 0ull;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) buf[base + __popc(m & ((1u << lane) - 1u))] = v[i];
+    base += __popc(m);
+  }
   __syncwarp();
-  return last != 0ull ? key_score(last) : -INFINITY;
+  return kth != 0ull ? key_score(kth) : -INFINITY;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MS_THREADS, 1)
@@ -276,7 +278,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const float thr = compact_buffer(my_cand + (int64_t)q * MS_CAP, min(cnt, MS_CAP), k, lane);
             if (lane == 0) {
               s_cnt[q] = min(cnt, k);
-              s_thr[q] = thr;
+              if (thr > s_thr[q]) s_thr[q] = thr;
             }
           }
         }
@@ -288,8 +290,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       unsigned long long* buf = my_cand + (int64_t)q * MS_CAP;
       const int cnt = s_cnt[q];
       if (cnt > k) compact_buffer(buf, min(cnt, MS_CAP), k, lane);
+      const int have = min(cnt, k);   // slots past `have` were never written: emit the empty key
       unsigned long long* o = dense + ((int64_t)q * gridDim.x + blockIdx.x) * k;
-      for (int j = lane; j < k; j += 32) o[j] = buf[j];
+      for (int j = lane; j < k; j += 32) o[j] = j < have ? buf[j] : 0ull;
     }
   }
 
@@ -320,7 +323,6 @@ int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const flo
     __half* Qp = (__half*)ws;
     unsigned long long* cand = (unsigned long long*)((char*)ws + qp_bytes);
     unsigned long long* dense = (unsigned long long*)((char*)ws + qp_bytes + cand_bytes);
-    B200_CUDA(cudaMemsetAsync(cand, 0, cand_bytes, st));
     {
       const int64_t total = (int64_t)groups * MS_QG * d;
       split_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q + (size_t)q0 * d, nqb, d, Qp, groups);

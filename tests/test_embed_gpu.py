@@ -184,6 +184,11 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
     out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
     check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), vt.data_ptr(), Tp, out.data_ptr(), B, T, heads, w, causal, 0,
                                             torch.cuda.current_stream().cuda_stream), "attention_tc")
+    # second variant: no V^T copy, V read from the qkv buffer as an MN-major tensor-core operand
+    out2 = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, 0, out2.data_ptr(), B, T, heads, w, causal, 0,
+                                            torch.cuda.current_stream().cuda_stream), "attention_tc")
+    assert torch.equal(out, out2), "V^T and MN-major V paths disagree: max diff %g" % (out.float() - out2.float()).abs().nan_to_num(1e9).max().item()
     q, k, vv = qkv.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-1, -2)) * hd ** -0.5
     if causal:
