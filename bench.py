@@ -261,7 +261,7 @@ def run_b200(args):
                     "api": "B200Clip.embed_image/embed_text (what ClipMapper.__call__ runs), pinned host tensors"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_bf16_tcgen05_kernel", "launches_per_step": gemm_launches,
+                         "traffic": None, "kernel": "gemm_bf16_tcgen05_pair_kernel (cta_group::2; the few small GEMMs use the single-CTA variant)", "launches_per_step": gemm_launches,
                          "peak_source": "%s bf16_tflops_sustained" % peaks["_source"],
                          "flops_per_step": gemm_flops, "gemm_ms_per_step": gemm_ms},
             "breakdown_ms_per_step": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "other": other_ms},
@@ -354,7 +354,7 @@ def run_knn(args, m, torch, dist, dev, local, rank, world, peaks, barrier, max_o
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(qh.nbytes), "d2h_bytes_per_step": int(D.nbytes + I.nbytes)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "traffic": None,
-                     "kernel": "flat_scan_kernel<1,3> (nq=1 serving shape)", "bytes_per_launch": bytes_per_launch,
+                     "kernel": "flat_scan_staged_kernel<1,3> (nq=1 serving shape, cp.async.bulk ring)", "bytes_per_launch": bytes_per_launch,
                      "batch_pass": {"achieved": achN, "frac": achN / peak, "launches_per_step": s_n},
                      "peak_source": "%s hbm_gbs" % peaks["_source"]},
     }

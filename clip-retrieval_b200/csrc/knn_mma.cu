@@ -18,6 +18,9 @@
 // that reaches the query's current threshold is appended to the (CTA, query) candidate buffer
 // (atomic counter in shared memory, buffer in global/L2); buffers are compacted to their k best by
 // the epilogue warps between tiles, which raises the threshold.  A final select merges the CTAs.
+// Thresholds are warmed up by two sampling passes (every 1024th, then every 32nd row tile: the k-th
+// best score of a subset is a valid lower bound for the full set), so the full pass almost never
+// takes the append path.
 // Roofline: tensor pipe (4*N*d*nq flops with the split) for large nq, HBM (N*d*2 bytes per 128
 // queries) below ~64 queries per pass.
 #include "index.cuh"
@@ -56,6 +59,14 @@ __global__ void split_queries_kernel(const float* __restrict__ Q, int nq, int d,
   const __half lo = __float2half_rn((v - __half2float(hi)) * 2048.0f);
   Qp[((int64_t)g * MS_BN + c) * d + j] = hi;
   Qp[((int64_t)g * MS_BN + MS_QG + c) * d + j] = lo;
+}
+
+// thr[q] = score of the k-th selected key of a sampling pass (a lower bound on the final k-th best)
+__global__ void kth_score_kernel(const unsigned long long* __restrict__ keys, int nq, int k, float* __restrict__ thr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const unsigned long long kk = keys[(int64_t)q * k + (k - 1)];
+  thr[q] = kk != 0ull ? key_score(kk) : -INFINITY;
 }
 
 // Keep the k best of a (CTA, query) candidate buffer (unsorted, in place, buf[0..k)); returns the
@@ -101,7 +112,8 @@ __device__ __forceinline__ float compact_buffer(unsigned long long* buf, int cou
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MS_THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n, int d,
                 int nq, int groups, int k, unsigned long long* __restrict__ cand /* [grid][groups*128][CAP] */,
-                unsigned long long* __restrict__ dense /* [nq][grid][k] */) {
+                unsigned long long* __restrict__ dense /* [nq][grid][k] */, int tile_stride,
+                const float* __restrict__ thr_init /* [nq] lower bounds on the k-th best score, or null */) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -125,7 +137,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int kb = (d + MS_BK - 1) / MS_BK;
 
   for (int i = threadIdx.x; i < groups * MS_QG; i += blockDim.x) {
-    s_thr[i] = -INFINITY;
+    s_thr[i] = (thr_init != nullptr && i < nq) ? thr_init[i] : -INFINITY;
     s_cnt[i] = 0;
   }
   if (warp == 0 && lane == 0) {
@@ -158,7 +170,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
+      for (int64_t rt = (int64_t)pair * tile_stride; rt < row_tiles; rt += (int64_t)npairs * tile_stride) {
         for (int g = 0; g < groups; g++) {
           for (int kbi = 0; kbi < kb; kbi++) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -180,7 +192,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
+      for (int64_t rt = (int64_t)pair * tile_stride; rt < row_tiles; rt += (int64_t)npairs * tile_stride) {
         for (int g = 0; g < groups; g++) {
           ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
@@ -211,7 +223,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     uint32_t acc_phase = 0;
     unsigned long long* my_cand = cand + (int64_t)blockIdx.x * groups * MS_QG * MS_CAP;
     const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
-    for (int64_t rt = pair; rt < row_tiles; rt += npairs) {
+    for (int64_t rt = (int64_t)pair * tile_stride; rt < row_tiles; rt += (int64_t)npairs * tile_stride) {
       const int64_t row = rt * 2 * MS_BM + rank * MS_BM + q4 * 32 + lane;
       const bool row_ok = row < n;
       for (int g = 0; g < groups; g++) {
@@ -340,17 +352,35 @@ int scan_topk_keys_mma(b200_index* idx, const __half* rows, int64_t n, const flo
       idx->ev.push_back(a);
       idx->ev.push_back(b);
     }
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
-    scan_mma_kernel<<<grid, MS_THREADS, smem, st>>>(tmX, tmQ, n, d, nqb, groups, k, cand, dense);
-    B200_LAUNCH_OK();
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
-    idx->ev_used += 2;
-    idx->last_scan_launches++;
-    // merge the per-CTA lists: grid*k candidates per query
+    // sampling passes first (strided row tiles), each seeding the next pass's thresholds
+    const int64_t row_tiles = (n + 2 * MS_BM - 1) / (2 * MS_BM);
     const int64_t M = (int64_t)grid * k;
     int C = 2048;
     while (C < 2 * k) C <<= 1;
-    B200_TRY(launch_topk_select(dense, M, M, k, C, d_keys_out + (size_t)q0 * k, k, 1, nqb, st));
+    void* wt = nullptr;
+    B200_TRY(index_ws(idx, 3, (size_t)nqb * 4 + 256, &wt));
+    float* thr = (float*)wt;
+    unsigned long long* keys_q = d_keys_out + (size_t)q0 * k;
+    const int strides[3] = {1024, 32, 1};
+    bool have_thr = false;
+    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
+    for (int pi = 0; pi < 3; pi++) {
+      const int stride = strides[pi];
+      if (stride > 1 && row_tiles / stride < (int64_t)(grid / 2) * 2) continue;  // too few tiles to be worth a pass
+      scan_mma_kernel<<<grid, MS_THREADS, smem, st>>>(tmX, tmQ, n, d, nqb, groups, k, cand, dense, stride,
+                                                      have_thr ? thr : nullptr);
+      B200_LAUNCH_OK();
+      idx->last_scan_launches++;
+      if (stride == 1) B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
+      // merge the per-CTA lists: grid*k candidates per query
+      B200_TRY(launch_topk_select(dense, M, M, k, C, keys_q, k, 1, nqb, st));
+      if (stride > 1) {
+        kth_score_kernel<<<(nqb + 255) / 256, 256, 0, st>>>(keys_q, nqb, k, thr);
+        B200_LAUNCH_OK();
+        have_thr = true;
+      }
+    }
+    idx->ev_used += 2;
   }
   return B200_OK;
 }
