@@ -76,6 +76,7 @@ struct b200_clip {
   std::mutex mu;
   // timing
   bool profiling = false;
+  bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
   bool attn_v_direct = true;   // P.V reads V from the qkv buffer as an MN-major operand (no V^T copy)
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -187,7 +188,9 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     }
     B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
-      if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
+      if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
+        B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+      else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
     B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st));
@@ -516,13 +519,17 @@ int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int
 
 int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads, int w,
                                   int causal, int device, void* stream) {
-  B200_CHECK(d_qkv && d_out && B >= 0 && T >= 1 && (d_vt == nullptr || (Tp >= T && Tp % 8 == 0)), B200_ERR_INVALID,
+  B200_CHECK(d_qkv && d_out && B >= 0 && T >= 1 && (d_vt == nullptr || (Tp >= T && Tp % 8 == 0)) && (Tp >= 0 || d_vt == nullptr), B200_ERR_INVALID,
              "attention_tc: bad argument");
   DeviceGuard g(device);
   CUtensorMap tq, tv;
   B200_TRY(make_tmap_2d(&tq, d_qkv, 1, (uint64_t)B * T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128, 64));
   if (d_vt) B200_TRY(make_tmap_2d(&tv, d_vt, 1, (uint64_t)B * heads * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 64));
   else tv = tq;
+  // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu)
+  if (Tp < 0)
+    return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
+                         (cudaStream_t)stream);
   // d_vt == NULL: V is read from the qkv buffer (MN-major operand); else from the V^T buffer
   return attention_tc(tq, tv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, d_vt == nullptr ? 1 : 0, sm_count(device),
                       (cudaStream_t)stream);

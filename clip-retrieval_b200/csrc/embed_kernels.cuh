@@ -24,6 +24,10 @@ int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int he
 bool attention_tc_supported(int T, int heads, int w);
 int attention_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVt, __nv_bfloat16* out, int B, int T, int heads, int w,
                  int causal, int v_direct, int sms, cudaStream_t st);
+// Two-tiles-in-flight variant (attention_tc2.cu): head dim 64, T <= 264; V read from the qkv buffer.
+bool attention_tc2_supported(int T, int heads, int w);
+int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
+                  int causal, int sms, cudaStream_t st);
 // K8/K10/K11: pooled row (x[b*T + pool_index(b)]) -> LN -> @ proj [w, D] -> optional L2 normalise
 // -> fp16 or fp32.  pool_idx == nullptr pools token 0 (vision); else row pool_idx[b] (text EOT).
 int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx, const float* gamma, const float* beta,

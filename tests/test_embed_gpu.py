@@ -166,7 +166,7 @@ def test_zero_feature_row_is_nan_like_reference():
 
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("B,T,heads,causal", [(2, 257, 16, 0), (3, 77, 8, 1), (2, 50, 12, 0), (1, 1, 2, 0), (5, 128, 4, 1),
-                                              (1, 320, 2, 0), (40, 257, 16, 0)])
+                                              (1, 320, 2, 0), (40, 257, 16, 0), (3, 260, 2, 0), (2, 256, 2, 1), (7, 129, 3, 0)])
 def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
     """tcgen05 attention (TMA K / V^T tiles, scores and output in TMEM, P through swizzled shared
     memory) against a plain fp32 PyTorch softmax(QK^T)V of the same bf16 inputs."""
@@ -197,3 +197,11 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
     err = (out.float() - ref).abs()
     assert not torch.isnan(out.float()).any()
     assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), "max err %g" % err.max().item()
+    if T <= 264:
+        # third variant: two query tiles in flight, keys past 256 on the FMA pipe (attention_tc2.cu)
+        out3 = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+        check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out3.data_ptr(), B, T, heads, w, causal, 0,
+                                                torch.cuda.current_stream().cuda_stream), "attention_tc2")
+        err3 = (out3.float() - ref).abs()
+        assert not torch.isnan(out3.float()).any()
+        assert bool((err3 <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc2 max err %g" % err3.max().item()

@@ -35,3 +35,12 @@ for (T, heads, causal) in ((257, 16, 0), (77, 12, 1)):
     e1.record()
     torch.cuda.synchronize()
     print("mma.sync variant: %.3f ms" % (e0.elapsed_time(e1) / reps))
+    if T <= 264:
+        for _ in range(2):
+            lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out.data_ptr(), B, T, heads, w, causal, 0, st)
+        e0.record()
+        for _ in range(reps):
+            lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out.data_ptr(), B, T, heads, w, causal, 0, st)
+        e1.record()
+        torch.cuda.synchronize()
+        print("tc2 (two tiles in flight): %.3f ms" % (e0.elapsed_time(e1) / reps))
