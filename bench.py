@@ -264,7 +264,8 @@ def run_b200(args):
                          "traffic": None, "kernel": "gemm_bf16_tcgen05_pair_kernel (cta_group::2; the few small GEMMs use the single-CTA variant)", "launches_per_step": gemm_launches,
                          "peak_source": "%s bf16_tflops_sustained" % peaks["_source"],
                          "flops_per_step": gemm_flops, "gemm_ms_per_step": gemm_ms},
-            "breakdown_ms_per_step": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "other": other_ms},
+            "breakdown_ms_per_step": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "other": other_ms,
+                                      "gemm_by_kind": {k: v / K for k, v in tm["gemm_by_kind"].items()}},
             "model_flops": {"per_pair": fl["pair"], "mfu_of_step": fl["pair"] * B / (ms_per_step / 1e3) / 1e12 / peak},
         })
         if clocks is not None:

@@ -214,52 +214,97 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
-        // pass 1: row maximum
-        float m = -INFINITY;
+        // Single read of the scores: the 256 key columns are taken in two blocks of 128 that live in
+        // registers between the block maximum and the exponentials (TMEM reads, 64 B/clk per SM, are the
+        // scarce resource: profiles/r01b).  Block 1 reuses block 0's reference maximum unless its own
+        // maximum is more than 2^8 above it; only then is block 0 redone against the new reference.
+        float mref = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
-#pragma unroll 1
-        for (int c = 0; c < chunks; c++) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
-          ptx::tmem_ld_wait();
-          const int lim = kmax - c * 32;
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
-            m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
-            m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
-            m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
-          }
-          m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        }
-        // pass 2: exponentials, row sum, P -> swizzled K-major tile of this group
-        const float mb = m * scale_log2e;
+        for (int e = 0; e < 8; e++) mref = fmaxf(mref, se[e]);
         float l0 = 0.f, l1 = 0.f;
+        float mb = 0.f;
+        const int nblk = (chunks + 3) / 4;
 #pragma unroll 1
-        for (int c = 0; c < chunks; c++) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+        for (int blk = 0; blk < nblk; blk++) {
+          const int cb = blk * 4;                                   // first 32-column chunk of the block
+          // always 4 chunks: columns past the keys are masked by `lim` (the buffer is 256 columns wide)
+          uint32_t v[4][32];
+#pragma unroll
+          for (int ci = 0; ci < 4; ci++) ptx::tmem_ld_32x32b_x32(tbase + (cb + ci) * 32, v[ci]);
           ptx::tmem_ld_wait();
-          const int lim = kmax - c * 32;
-          uint32_t pk[16];
+          float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0, p1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
-            p0 = j <= lim ? p0 : 0.f;
-            p1 = j + 1 <= lim ? p1 : 0.f;
-            l0 += p0;
-            l1 += p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
+          for (int ci = 0; ci < 4; ci++) {
+            const int lim = kmax - (cb + ci) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              bm0 = fmaxf(bm0, j + 0 <= lim ? __uint_as_float(v[ci][j + 0]) : -INFINITY);
+              bm1 = fmaxf(bm1, j + 1 <= lim ? __uint_as_float(v[ci][j + 1]) : -INFINITY);
+              bm2 = fmaxf(bm2, j + 2 <= lim ? __uint_as_float(v[ci][j + 2]) : -INFINITY);
+              bm3 = fmaxf(bm3, j + 3 <= lim ? __uint_as_float(v[ci][j + 3]) : -INFINITY);
+            }
           }
-          uint8_t* blk = sPg + (c >> 1) * (128 * 128) + r * 128;
+          const float bmax = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
+          if (blk == 0) {
+            mref = fmaxf(mref, bmax);
+          } else if ((bmax - mref) * scale_log2e > 8.0f) {
+            // rare: block `blk` towers over the reference.  Redo the earlier blocks' P against the new
+            // reference (their scores are still in TMEM: O only overwrites them after p_full).
+            const float mnew = bmax;
+            l0 = 0.f;
+            l1 = 0.f;
+            const float mbn = mnew * scale_log2e;
+            for (int c = 0; c < cb; c++) {
+              uint32_t t[32];
+              ptx::tmem_ld_32x32b_x32(tbase + c * 32, t);
+              ptx::tmem_ld_wait();
+              const int lim = kmax - c * 32;
+              uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
-            *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+              for (int j = 0; j < 32; j += 2) {
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(t[j]), scale_log2e, -mbn)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(t[j + 1]), scale_log2e, -mbn)));
+                p0 = j <= lim ? p0 : 0.f;
+                p1 = j + 1 <= lim ? p1 : 0.f;
+                l0 += p0;
+                l1 += p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+              uint8_t* blkp = sPg + (c >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
+                *reinterpret_cast<uint4*>(blkp + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+              }
+            }
+            mref = mnew;
+          }
+          mb = mref * scale_log2e;
+#pragma unroll
+          for (int ci = 0; ci < 4; ci++) {
+            {
+              const int c = cb + ci;
+              const int lim = kmax - c * 32;
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[ci][j]), scale_log2e, -mb)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[ci][j + 1]), scale_log2e, -mb)));
+                p0 = j <= lim ? p0 : 0.f;
+                p1 = j + 1 <= lim ? p1 : 0.f;
+                l0 += p0;
+                l1 += p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+              uint8_t* blkp = sPg + (c >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
+                *reinterpret_cast<uint4*>(blkp + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+              }
+            }
           }
         }
         float pe[8];

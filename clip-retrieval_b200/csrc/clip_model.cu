@@ -46,7 +46,8 @@ struct Tower {
   __nv_bfloat16* proj = nullptr;             // [width, D]
 };
 
-enum { CLS_GEMM = 0, CLS_ATTN = 1, CLS_LN = 2, CLS_OTHER = 3 };
+enum { CLS_GEMM = 0, CLS_ATTN = 1, CLS_LN = 2, CLS_OTHER = 3,
+       CLS_G_QKV = 4, CLS_G_OUT = 5, CLS_G_FC = 6, CLS_G_PROJ = 7, CLS_COUNT = 8 };  // 4..7: per-kind share of CLS_GEMM
 
 }  // namespace b200
 
@@ -167,8 +168,9 @@ struct SpanGuard {
   }
 };
 
-static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int M, GemmEpilogue ep, cudaStream_t st) {
-  SpanGuard sg(m, CLS_GEMM, st);
+static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int M, GemmEpilogue ep, cudaStream_t st,
+                      int kind = CLS_GEMM) {
+  SpanGuard sg(m, kind, st);
   const int bn = gemm_pick_bn(M, l.N, m->sms);
   ep.bias = l.b;
   m->last_launches++;
@@ -186,20 +188,20 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     if (t.use_tc_attn && !m->attn_v_direct) {
       e1.vt = t.vt; e1.vt_col0 = 2 * w; e1.vt_T = t.T; e1.vt_Tp = t.Tp; e1.vt_hd = 64; e1.vt_heads = t.heads;
     }
-    B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st));
+    B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
         B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
-    B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st));
+    B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st, CLS_G_OUT));
     { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln2_g, L.ln2_b, M, w, st)); }
     GemmEpilogue e3; e3.out = t.f; e3.out_ld = t.mlp; e3.act = act;
-    B200_TRY(run_linear(m, t.tm_h, L.fc, M, e3, st));
+    B200_TRY(run_linear(m, t.tm_h, L.fc, M, e3, st, CLS_G_FC));
     GemmEpilogue e4; e4.out = t.x; e4.out_ld = w; e4.residual = t.x; e4.res_ld = w;
-    B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st));
+    B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st, CLS_G_PROJ));
   }
   return B200_OK;
 }
@@ -545,13 +547,14 @@ int b200_clip_set_profiling(b200_clip* m, int on) {
 int b200_clip_last_timing(b200_clip* m, float* ms_by_class, int* launches) {
   B200_CHECK(m && ms_by_class, B200_ERR_INVALID, "last_timing: null argument");
   DeviceGuard g(m->device);
-  for (int i = 0; i < 4; i++) ms_by_class[i] = 0.f;
+  for (int i = 0; i < CLS_COUNT; i++) ms_by_class[i] = 0.f;
   for (int i = 0; i < m->span_used; i++) {
     const auto& s = m->spans[i];
     B200_CUDA(cudaEventSynchronize(s.b));
     float t = 0.f;
     B200_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
-    if (s.cls >= 0 && s.cls < 4) ms_by_class[s.cls] += t;
+    if (s.cls >= 0 && s.cls < CLS_COUNT) ms_by_class[s.cls] += t;
+    if (s.cls >= CLS_G_QKV && s.cls <= CLS_G_PROJ) ms_by_class[CLS_GEMM] += t;
   }
   if (launches) *launches = m->span_used;
   m->span_used = 0;

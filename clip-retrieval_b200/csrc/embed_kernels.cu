@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels of the embed path: im2col, embeddings, LayerNorm, pooled projection +
 // L2-normalise + cast (reference mapper.py:58-59,66-67).  All statistics in fp32.
 #include "embed_kernels.cuh"
+#include <algorithm>
 
 namespace b200 {
 
@@ -108,46 +109,14 @@ template <int CPL>          // chunks per lane actually present: ceil(w / 256)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloat16* __restrict__ out, int64_t out_ld,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int w) {
+  // persistent warps: row = gwarp, gwarp + total, ...; the next row's 16-byte chunks are loaded
+  // before the current row is reduced and stored, so a warp always has a row in flight.
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int chunks = w >> 3;
-  const __nv_bfloat16* src = in + row * in_ld;
-  float v[CPL][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < CPL; c++) {
-    const int ci = c * 32 + lane;
-    if (ci < chunks) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + ci * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float2 f = __bfloat1622float2(h[j]);
-        v[c][2 * j] = f.x;
-        v[c][2 * j + 1] = f.y;
-        sum += f.x + f.y;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)w;
-  float ss = 0.f;
-#pragma unroll
-  for (int c = 0; c < CPL; c++) {
-    if (c * 32 + lane < chunks) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float dlt = v[c][j] - mean;
-        ss += dlt * dlt;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / (float)w + 1e-5f);
-  __nv_bfloat16* dst = out + row * out_ld;
+  // affine parameters of this lane's columns stay in registers across rows
+  float gg[CPL][8], bb[CPL][8];
 #pragma unroll
   for (int c = 0; c < CPL; c++) {
     const int ci = c * 32 + lane;
@@ -156,17 +125,76 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int64_t in_ld, __nv_bfloa
       const float4 g1 = *reinterpret_cast<const float4*>(gamma + ci * 8 + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(beta + ci * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(beta + ci * 8 + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t o[4];
+      gg[c][0] = g0.x; gg[c][1] = g0.y; gg[c][2] = g0.z; gg[c][3] = g0.w;
+      gg[c][4] = g1.x; gg[c][5] = g1.y; gg[c][6] = g1.z; gg[c][7] = g1.w;
+      bb[c][0] = b0.x; bb[c][1] = b0.y; bb[c][2] = b0.z; bb[c][3] = b0.w;
+      bb[c][4] = b1.x; bb[c][5] = b1.y; bb[c][6] = b1.z; bb[c][7] = b1.w;
+    }
+  }
+  uint4 nxt[CPL];
+  if (gw < rows) {
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int ci = c * 32 + lane;
+      nxt[c] = ci < chunks ? *reinterpret_cast<const uint4*>(in + gw * in_ld + ci * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  for (int64_t row = gw; row < rows; row += total) {
+    uint4 cur[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) cur[c] = nxt[c];
+    if (row + total < rows) {
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const int ci = c * 32 + lane;
+        nxt[c] = ci < chunks ? *reinterpret_cast<const uint4*>(in + (row + total) * in_ld + ci * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float v[CPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[c]);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const float a = (v[c][2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j];
-        const float b = (v[c][2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
-        __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-        o[j] = *reinterpret_cast<uint32_t*>(&t);
+        const float2 f = __bfloat1622float2(h[j]);
+        v[c][2 * j] = f.x;
+        v[c][2 * j + 1] = f.y;
+        sum += f.x + f.y;   // chunks past the row are zeros
       }
-      *reinterpret_cast<uint4*>(dst + ci * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)w;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      if (c * 32 + lane < chunks) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float dlt = v[c][j] - mean;
+          ss += dlt * dlt;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)w + 1e-5f);
+    __nv_bfloat16* dst = out + row * out_ld;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      const int ci = c * 32 + lane;
+      if (ci < chunks) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float a = (v[c][2 * j] - mean) * rstd * gg[c][2 * j] + bb[c][2 * j];
+          const float b = (v[c][2 * j + 1] - mean) * rstd * gg[c][2 * j + 1] + bb[c][2 * j + 1];
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+          o[j] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(dst + ci * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
@@ -174,7 +202,8 @@ int layernorm_rows(const __nv_bfloat16* in, int64_t in_ld, __nv_bfloat16* out, i
                    const float* beta, int64_t rows, int w, cudaStream_t st) {
   B200_CHECK(w % 8 == 0 && w <= LN_MAXC * 256, B200_ERR_UNSUPPORTED, "layernorm: width %d (need %%8, <= 2048)", w);
   if (rows == 0) return B200_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  // persistent: enough blocks to fill the chip, each warp strides over rows
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)148 * 6);
   switch ((w / 8 + 31) / 32) {
     case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;
     case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, gamma, beta, rows, w); break;

@@ -47,11 +47,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   const int mb = (M + G2_BM - 1) / G2_BM, nb = (N + G2_BN - 1) / G2_BN, kb = (K + GEMM_BK - 1) / GEMM_BK;
   const int tiles = mb * nb;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_WARP_TMA && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
   }
-  if (warp == 1) {
+  if (warp == GEMM_WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < G2_STAGES; s++) {
         ptx::mbar_init(&full[s], 1);   // the leader's producer arrives; both CTAs' TMA bytes are credited here
@@ -72,7 +72,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
+  if (warp == GEMM_WARP_TMA) {
     // ---------------- TMA producer (both CTAs) ----------------
     if (lane == 0) {
       int stage = 0;
@@ -80,7 +80,16 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       for (int tile = pair; tile < tiles; tile += npairs) {
         int m_blk, n_blk;
         gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
+        // the pair's next tile: pull its A rows towards L2 a whole tile ahead when they are new (first
+        // column block of a row group), so the 6-stage ring does not have to cover HBM latency
+        int m_nxt = -1;
+        if (tile + npairs < tiles) {
+          int mn, nn;
+          gemm_tile_coords(tile + npairs, mb, nb, mn, nn);
+          if (nn == 0) m_nxt = mn;
+        }
         for (int kbi = 0; kbi < kb; kbi++) {
+          if (m_nxt >= 0) ptx::tma_prefetch_2d(&tmA, kbi * GEMM_BK, m_nxt * G2_BM + (int)rank * 128);
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, &full[stage], kbi * GEMM_BK,
                                 m_blk * G2_BM + (int)rank * 128);
@@ -94,7 +103,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == GEMM_WARP_MMA) {
     // ---------------- MMA issuer (leader CTA only) ----------------
     if (leader && lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16(G2_BM, G2_BN, true);
@@ -126,8 +135,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   } else {
     // ---------------- epilogue (warps 2..5 of both CTAs) ----------------
     const int q = warp & 3;
-    const int et = (warp - 2) * 32 + lane;  // 0..255
-    const int half = (warp - 2) >> 2;        // which half of the tile columns this warp drains
+    const int et = warp * 32 + lane;  // 0..255 (epilogue warps are warps 0..7)
+    const int half = warp >> 2;        // which half of the tile columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
@@ -140,19 +149,32 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       for (int j = et; j < G2_BN; j += 256) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
-      ptx::mbar_wait(&tfull[acc], acc_phase);
-      ptx::tc_fence_after();
-
       const int row = m_blk * G2_BM + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = row < M;
       const EpiRow er = epi_row(ep, row, n0);
+      constexpr int CPW = G2_BN / 64;   // 32-column chunks per epilogue warp
+      // residual prefetch: issued before the accumulator wait so its latency overlaps the main loop
+      uint4 res[CPW][4];
+#pragma unroll
+      for (int ci = 0; ci < CPW; ci++) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int col = (half * CPW + ci) * 32 + g * 8;
+          res[ci][g] = (row_ok && er.res_ptr != nullptr && n0 + col < N)
+                           ? *reinterpret_cast<const uint4*>(er.res_ptr + col) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
 
-#pragma unroll 1
-      for (int c = half * (G2_BN / 64); c < (half + 1) * (G2_BN / 64); c++) {
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+
+#pragma unroll
+      for (int ci = 0; ci < CPW; ci++) {
+        const int c = half * CPW + ci;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
         ptx::tmem_ld_wait();
-        if (c == (half + 1) * (G2_BN / 64) - 1) {
+        if (ci == CPW - 1) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -164,7 +186,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             const int col = c * 32 + g * 8;
-            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0);
+            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0, res[ci][g]);
           }
         }
       }
@@ -175,7 +197,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 
   ptx::tc_fence_before();
   ptx::cluster_sync_all();
-  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
+  if (warp == GEMM_WARP_MMA) ptx::tmem_dealloc_pair(tmem_base, 512);
 }
 
 }  // namespace b200

@@ -282,10 +282,11 @@ class B200Clip:
         check(lib.b200_clip_set_profiling(self._h, 1 if on else 0), "set_profiling")
 
     def last_timing(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 8)()
         n = C.c_int(0)
         check(lib.b200_clip_last_timing(self._h, ms, C.byref(n)), "last_timing")
-        return {"gemm": ms[0], "attention": ms[1], "layernorm": ms[2], "other": ms[3], "launches": int(n.value)}
+        return {"gemm": ms[0], "attention": ms[1], "layernorm": ms[2], "other": ms[3], "launches": int(n.value),
+                "gemm_by_kind": {"qkv": ms[4], "out_proj": ms[5], "fc": ms[6], "c_proj": ms[7]}}
 
 
 def _is_torch(x):

@@ -177,7 +177,8 @@ int b200_clip_encode_text(b200_clip* m, const int64_t* h_tokens, int B, void* h_
 /* Per-kernel-class device time (ms, CUDA events on the launching stream) accumulated over the encode
  * calls since profiling was switched on or since the previous read: gemm, attention, layernorm,
  * other; `spans` = number of timed kernel groups.  Synchronises on the events, then resets. */
-int b200_clip_last_timing(b200_clip* m, float* ms_by_class /*[4]*/, int* spans);
+int b200_clip_last_timing(b200_clip* m, float* ms_by_class /*[8]: gemm, attention, layernorm, other, then the
+                             gemm share of qkv / out-proj / fc / c_proj */, int* spans);
 /* Enable per-class event timing (event records between kernels; off by default); resets the sums. */
 int b200_clip_set_profiling(b200_clip* m, int on);
 

@@ -205,3 +205,28 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
         err3 = (out3.float() - ref).abs()
         assert not torch.isnan(out3.float()).any()
         assert bool((err3 <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc2 max err %g" % err3.max().item()
+
+
+@pytest.mark.timeout(120)
+def test_tcgen05_attention_second_key_block_dominates():
+    """attention_tc2 keeps block 0's reference maximum for block 1 unless block 1 towers over it by more
+    than 2^8; this input (keys >= 128 scaled up) forces the redo path, plus rows where it is not taken."""
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    B, T, heads, hd = 3, 257, 4, 64
+    w = heads * hd
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(B * T, 3 * w, device="cuda", generator=g)
+    kview = qkv.view(B, T, 3, heads, hd)
+    kview[0, 128:, 1] *= 6.0          # sample 0: every row sees much larger scores in the second block
+    kview[1, 200:230, 1, 0] *= 6.0    # sample 1, head 0 only
+    qkv = qkv.bfloat16()
+    out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out.data_ptr(), B, T, heads, w, 0, 0,
+                                            torch.cuda.current_stream().cuda_stream), "attention_tc2")
+    q, k, vv = qkv.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, -1) @ vv).transpose(1, 2).reshape(B * T, w)
+    err = (out.float() - ref).abs()
+    assert not torch.isnan(out.float()).any()
+    assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), "max err %g" % err.max().item()
