@@ -92,6 +92,7 @@ PROTOTYPES = {
     "b200_index_ivf_lists": (_i, [_vp, _vp, _vp]),
     "b200_index_search": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200_index_search_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200_index_range_search": (_i, [_vp, _vp, C.c_float, _i64, _vp, _vp, C.POINTER(_i64)]),
     "b200_index_reconstruct_device": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "b200_topk_merge_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200_index_last_scan_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -10,11 +10,11 @@
 // exp pass.  Keys past 256 (the cls token makes T = 257) never touch the tensor core: their scores
 // q.k_e and their p_e*v_e contributions are a 64-term dot product per row on the FMA pipe.
 //
-//   warp 0      TMA: K, V rows of the head (128-row boxes) once per (sample, head),
+//   warp 8      TMA: K, V rows of the head (128-row boxes) once per (sample, head),
 //               Q tile per 128 query rows; all straight out of the fused qkv buffer, 128B swizzle.
-//   warp 1      tcgen05.mma issuer: S(t) = Q K^T (128 x keys x 16, K-major), O(t) = P V with V as an
+//   warp 9      tcgen05.mma issuer: S(t) = Q K^T (128 x keys x 16, K-major), O(t) = P V with V as an
 //               MN-major operand; order S(t), PV(t-1), S(t+1), PV(t), ...
-//   warps 2..5  softmax group 0 (even tiles), warps 6..9 group 1 (odd tiles): thread = query row:
+//   warps 0..3  softmax group 0 (even tiles), warps 4..7 group 1 (odd tiles): thread = query row:
 //               row max, ex2.approx, row sum, P as bf16 into the swizzled K-major smem tile of the
 //               group, then O * (1/l) -> bf16 -> global.
 #include "embed_kernels.cuh"
@@ -62,10 +62,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   const int q_tiles = (T + 127) / 128;
   const int items = B * heads;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tensormap(&tmBig);
   }
-  if (warp == 1) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int i = 0; i < 6; i++) ptx::mbar_init(&bars[i], 1);
       for (int i = 0; i < 2; i++) {
@@ -85,7 +85,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
+  if (warp == 8) {  // the single-thread roles use the highest warp ids (arbiter priority)
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
@@ -112,7 +112,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc_s = ptx::umma_idesc_f16(128, keys_main, true);
@@ -165,7 +165,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
     __syncwarp();
   } else {
     // ---------------- softmax groups ----------------
-    const int grp = (warp - 2) >> 2;               // 0: even tiles, 1: odd tiles
+    const int grp = warp >> 2;                     // 0: even tiles, 1: odd tiles
     const int q4 = warp & 3;                       // TMEM lane quarter
     const int r = q4 * 32 + lane;                  // row inside the tile
     const uint32_t tbase = tmem_base + grp * 256 + ((uint32_t)(q4 * 32) << 16);
@@ -214,98 +214,71 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
-        // Single read of the scores: the 256 key columns are taken in two blocks of 128 that live in
-        // registers between the block maximum and the exponentials (TMEM reads, 64 B/clk per SM, are the
-        // scarce resource: profiles/r01b).  Block 1 reuses block 0's reference maximum unless its own
-        // maximum is more than 2^8 above it; only then is block 0 redone against the new reference.
-        float mref = -INFINITY;
+        // Both passes read the scores chunk by chunk (32 columns) with the NEXT chunk's tcgen05.ld already
+        // in flight while the current one is processed (two register buffers), so the TMEM latency is
+        // off the critical path and only its bandwidth remains.
+        auto chunk_max = [&](const uint32_t (&v)[32], int c, float& mm) {
+          const int lim = kmax - c * 32;   // columns j <= lim are visible
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 8; e++) mref = fmaxf(mref, se[e]);
-        float l0 = 0.f, l1 = 0.f;
-        float mb = 0.f;
-        const int nblk = (chunks + 3) / 4;
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
+            m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
+            m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
+            m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
+          }
+          mm = fmaxf(mm, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        };
+        // pass 1: row maximum
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32b_x32(tbase, va);
+        ptx::tmem_ld_wait();
 #pragma unroll 1
-        for (int blk = 0; blk < nblk; blk++) {
-          const int cb = blk * 4;                                   // first 32-column chunk of the block
-          // always 4 chunks: columns past the keys are masked by `lim` (the buffer is 256 columns wide)
-          uint32_t v[4][32];
-#pragma unroll
-          for (int ci = 0; ci < 4; ci++) ptx::tmem_ld_32x32b_x32(tbase + (cb + ci) * 32, v[ci]);
+        for (int c = 0; c < chunks; c += 2) {
+          if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
+          chunk_max(va, c, m);
           ptx::tmem_ld_wait();
-          float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+          if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
+          if (c + 1 < chunks) chunk_max(vb, c + 1, m);
+          ptx::tmem_ld_wait();
+        }
+        // pass 2: exponentials, row sum, P -> swizzled K-major tile of this group
+        const float mb = m * scale_log2e;
+        float l0 = 0.f, l1 = 0.f;
+        auto chunk_exp = [&](const uint32_t (&v)[32], int c) {
+          const int lim = kmax - c * 32;
+          uint32_t pk[16];
 #pragma unroll
-          for (int ci = 0; ci < 4; ci++) {
-            const int lim = kmax - (cb + ci) * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              bm0 = fmaxf(bm0, j + 0 <= lim ? __uint_as_float(v[ci][j + 0]) : -INFINITY);
-              bm1 = fmaxf(bm1, j + 1 <= lim ? __uint_as_float(v[ci][j + 1]) : -INFINITY);
-              bm2 = fmaxf(bm2, j + 2 <= lim ? __uint_as_float(v[ci][j + 2]) : -INFINITY);
-              bm3 = fmaxf(bm3, j + 3 <= lim ? __uint_as_float(v[ci][j + 3]) : -INFINITY);
-            }
+          for (int j = 0; j < 32; j += 2) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
+            p0 = j <= lim ? p0 : 0.f;
+            p1 = j + 1 <= lim ? p1 : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
           }
-          const float bmax = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
-          if (blk == 0) {
-            mref = fmaxf(mref, bmax);
-          } else if ((bmax - mref) * scale_log2e > 8.0f) {
-            // rare: block `blk` towers over the reference.  Redo the earlier blocks' P against the new
-            // reference (their scores are still in TMEM: O only overwrites them after p_full).
-            const float mnew = bmax;
-            l0 = 0.f;
-            l1 = 0.f;
-            const float mbn = mnew * scale_log2e;
-            for (int c = 0; c < cb; c++) {
-              uint32_t t[32];
-              ptx::tmem_ld_32x32b_x32(tbase + c * 32, t);
-              ptx::tmem_ld_wait();
-              const int lim = kmax - c * 32;
-              uint32_t pk[16];
+          uint8_t* blk = sPg + (c >> 1) * (128 * 128) + r * 128;
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(t[j]), scale_log2e, -mbn)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(t[j + 1]), scale_log2e, -mbn)));
-                p0 = j <= lim ? p0 : 0.f;
-                p1 = j + 1 <= lim ? p1 : 0.f;
-                l0 += p0;
-                l1 += p1;
-                pk[j >> 1] = pack_bf16x2(p0, p1);
-              }
-              uint8_t* blkp = sPg + (c >> 1) * (128 * 128) + r * 128;
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
-                *reinterpret_cast<uint4*>(blkp + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
-              }
-            }
-            mref = mnew;
+          for (int i = 0; i < 4; i++) {
+            const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
+            *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
           }
-          mb = mref * scale_log2e;
-#pragma unroll
-          for (int ci = 0; ci < 4; ci++) {
-            {
-              const int c = cb + ci;
-              const int lim = kmax - c * 32;
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[ci][j]), scale_log2e, -mb)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[ci][j + 1]), scale_log2e, -mb)));
-                p0 = j <= lim ? p0 : 0.f;
-                p1 = j + 1 <= lim ? p1 : 0.f;
-                l0 += p0;
-                l1 += p1;
-                pk[j >> 1] = pack_bf16x2(p0, p1);
-              }
-              uint8_t* blkp = sPg + (c >> 1) * (128 * 128) + r * 128;
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
-                *reinterpret_cast<uint4*>(blkp + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
-              }
-            }
-          }
+        };
+        ptx::tmem_ld_32x32b_x32(tbase, va);
+        ptx::tmem_ld_wait();
+#pragma unroll 1
+        for (int c = 0; c < chunks; c += 2) {
+          if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
+          chunk_exp(va, c);
+          ptx::tmem_ld_wait();
+          if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
+          if (c + 1 < chunks) chunk_exp(vb, c + 1);
+          ptx::tmem_ld_wait();
         }
         float pe[8];
 #pragma unroll
@@ -367,7 +340,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 bool attention_tc2_supported(int T, int heads, int w) {

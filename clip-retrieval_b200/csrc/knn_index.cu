@@ -20,6 +20,8 @@ int ivf_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth
 int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned long long* d_keys, cudaStream_t st);
 int ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
 void ivf_free(b200_index* idx);
+int range_scan(b200_index* idx, const __half* rows, int64_t n, const float* d_q, float thresh, unsigned long long* d_out,
+               unsigned int cap, unsigned int* d_count, cudaStream_t st);
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +353,37 @@ int b200_index_search(b200_index* idx, const float* h_q, int nq, int k, float* h
   B200_CUDA(cudaMemcpyAsync(h_I, d_I, ib, cudaMemcpyDeviceToHost, 0));
   if (h_R) B200_CUDA(cudaMemcpyAsync(h_R, d_R, rb, cudaMemcpyDeviceToHost, 0));
   B200_CUDA(cudaStreamSynchronize(0));
+  return B200_OK;
+}
+
+int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int64_t cap, float* h_D, int64_t* h_I,
+                            int64_t* h_count) {
+  B200_CHECK(idx && h_q && h_count && cap >= 0 && (cap == 0 || (h_D && h_I)), B200_ERR_INVALID, "range_search: bad argument");
+  B200_CHECK(idx->nlist == 0, B200_ERR_UNSUPPORTED, "range_search is implemented for the flat index");
+  B200_CHECK(cap < (1ll << 31), B200_ERR_INVALID, "range_search: cap too large");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  DeviceGuard g(idx->device);
+  const size_t qb = ((size_t)idx->d * 4 + 255) & ~(size_t)255;
+  void* ws = nullptr;
+  B200_TRY(index_ws(idx, 2, qb + 256 + (size_t)cap * 8 + (size_t)cap * 12, &ws));
+  float* d_q = (float*)ws;
+  unsigned int* d_count = (unsigned int*)((char*)ws + qb);
+  unsigned long long* d_keys = (unsigned long long*)((char*)ws + qb + 256);
+  float* d_D = (float*)(d_keys + cap);
+  int64_t* d_I = (int64_t*)((char*)d_D + (((size_t)cap * 4 + 7) & ~(size_t)7));
+  B200_CUDA(cudaMemcpyAsync(d_q, h_q, (size_t)idx->d * 4, cudaMemcpyHostToDevice, 0));
+  B200_TRY(range_scan(idx, idx->rows, idx->ntotal, d_q, thresh, d_keys, (unsigned int)cap, d_count, 0));
+  unsigned int cnt = 0;
+  B200_CUDA(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, 0));
+  B200_CUDA(cudaStreamSynchronize(0));
+  *h_count = cnt;
+  const int64_t m = std::min<int64_t>(cnt, cap);
+  if (m > 0) {
+    B200_TRY(decode_keys(d_keys, m, idx->id_base, nullptr, d_D, d_I, 0));
+    B200_CUDA(cudaMemcpyAsync(h_D, d_D, (size_t)m * 4, cudaMemcpyDeviceToHost, 0));
+    B200_CUDA(cudaMemcpyAsync(h_I, d_I, (size_t)m * 8, cudaMemcpyDeviceToHost, 0));
+    B200_CUDA(cudaStreamSynchronize(0));
+  }
   return B200_OK;
 }
 

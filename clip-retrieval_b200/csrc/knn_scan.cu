@@ -549,3 +549,87 @@ int decode_keys(const unsigned long long* keys, int64_t count, int64_t id_base, 
 }
 
 }  // namespace b200
+
+// ---- range search (index.range_search: clip_filter.py:52, clip_back.py:294) ---------------------------
+// All rows whose score with the query exceeds `thresh`: same warp-per-4-rows scan, hits appended
+// to a global (row, score) list per query through one atomic counter.  Results are unordered (FAISS
+// leaves the order within a query unspecified); the host wrapper sorts them by id.
+namespace b200 {
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+range_scan_kernel(const uint4* __restrict__ X, int64_t n, int cpr, const float* __restrict__ Q, float thresh,
+                  unsigned long long* __restrict__ out, unsigned int cap, unsigned int* __restrict__ counter) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float qr[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    const int ci = c * 32 + lane;
+    if (ci < cpr) {
+      const float4 a = *reinterpret_cast<const float4*>(Q + ci * 8);
+      const float4 b = *reinterpret_cast<const float4*>(Q + ci * 8 + 4);
+      qr[c][0] = a.x; qr[c][1] = a.y; qr[c][2] = a.z; qr[c][3] = a.w;
+      qr[c][4] = b.x; qr[c][5] = b.y; qr[c][6] = b.z; qr[c][7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) qr[c][j] = 0.f;
+    }
+  }
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, total = (int64_t)gridDim.x * nwarps;
+  const int64_t nblk = (n + 3) / 4;
+  for (int64_t blk = gw; blk < nblk; blk += total) {
+    const int64_t r0 = blk * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int ci = c * 32 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + u < n && ci < cpr) v = ld_nc_v4(X + (r0 + u) * cpr + ci);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 t = __half22float2(h2[j]);
+          acc[u] = fmaf(t.x, qr[c][2 * j], acc[u]);
+          acc[u] = fmaf(t.y, qr[c][2 * j + 1], acc[u]);
+        }
+      }
+    }
+    warp_transpose_reduce<4>(acc, lane);
+    const int64_t my_r = r0 + (lane >> 3);
+    if ((lane & 7) == 0 && my_r < n && acc[0] > thresh) {
+      const unsigned int pos = atomicAdd(counter, 1u);
+      if (pos < cap) out[pos] = make_key(acc[0], (uint32_t)my_r);
+    }
+  }
+}
+
+typedef void (*range_fn)(const uint4*, int64_t, int, const float*, float, unsigned long long*, unsigned int, unsigned int*);
+static range_fn pick_range(int ch) {
+  switch (ch) {
+    case 1: return range_scan_kernel<1>;
+    case 2: return range_scan_kernel<2>;
+    case 3: return range_scan_kernel<3>;
+    case 4: return range_scan_kernel<4>;
+    case 5: return range_scan_kernel<5>;
+    case 6: return range_scan_kernel<6>;
+    case 7: return range_scan_kernel<7>;
+    case 8: return range_scan_kernel<8>;
+  }
+  return nullptr;
+}
+
+// One query: appends up to `cap` keys to d_out, *d_count receives the number of hits (may exceed cap).
+int range_scan(b200_index* idx, const __half* rows, int64_t n, const float* d_q, float thresh, unsigned long long* d_out,
+               unsigned int cap, unsigned int* d_count, cudaStream_t st) {
+  const int ch = (idx->d / 8 + 31) / 32;
+  range_fn fn = pick_range(ch);
+  B200_CHECK(fn != nullptr, B200_ERR_UNSUPPORTED, "range_search: unsupported dimension %d", idx->d);
+  B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), st));
+  fn<<<idx->sms * 4, 256, 0, st>>>(reinterpret_cast<const uint4*>(rows), n, idx->d / 8, d_q, thresh, d_out, cap, d_count);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+}  // namespace b200

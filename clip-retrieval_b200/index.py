@@ -196,6 +196,31 @@ class B200FlatIndex(_IndexBase):
         self.device = device
         check(lib.b200_index_create_flat(int(d), int(device), C.byref(self._h)), "create_flat")
 
+    def range_search(self, x, thresh):
+        """index.range_search(x, thresh) -> (lims, D, I): every row with inner product > thresh, per
+        query (clip_filter.py:52; the dedup of clip_back.py:294).  Within a query results are sorted by id."""
+        x = _as_query(x, self.d)
+        lims = [0]
+        Ds, Is = [], []
+        for q in range(x.shape[0]):
+            cap = 4096
+            while True:
+                D = np.empty(cap, dtype=np.float32)
+                I = np.empty(cap, dtype=np.int64)
+                cnt = C.c_int64(0)
+                check(lib.b200_index_range_search(self._h, x[q].ctypes.data, float(thresh), cap, D.ctypes.data, I.ctypes.data,
+                                                  C.byref(cnt)), "range_search")
+                if cnt.value <= cap:
+                    break
+                cap = int(cnt.value)
+            n = int(cnt.value)
+            order = np.argsort(I[:n], kind="stable")
+            Ds.append(D[:n][order])
+            Is.append(I[:n][order])
+            lims.append(lims[-1] + n)
+        return (np.asarray(lims, dtype=np.uint64), np.concatenate(Ds) if Ds else np.empty(0, np.float32),
+                np.concatenate(Is) if Is else np.empty(0, np.int64))
+
     def reconstruct(self, key):
         torch = _torch()
         ids = torch.tensor([int(key)], dtype=torch.int64, device="cuda:%d" % self.device)

@@ -114,6 +114,12 @@ int b200_index_search(b200_index* idx, const float* h_q, int nq, int k,
 /* Same with DEVICE buffers, asynchronous on `stream`. */
 int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k,
                              float* d_D, int64_t* d_I, float* d_R, void* stream);
+/* index.range_search(x, thresh) for ONE query (flat index; reference call sites clip_filter.py:52 and
+ * clip_back.py:294): every row whose inner product with h_q exceeds `thresh`.  At most `cap` results
+ * are written (h_D/h_I, unordered); *h_count receives the true number of hits, so a caller that sees
+ * *h_count > cap retries with a larger buffer. */
+int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int64_t cap, float* h_D, int64_t* h_I,
+                            int64_t* h_count);
 /* reconstruct(id) for a batch of ids (device buffers): d_R [n, d] fp32; id -1 -> NaN row. */
 int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t n, float* d_R, void* stream);
 /* Merge G sorted candidate lists per query into one top-k (the step after the all-gather of

@@ -209,8 +209,8 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
 
 @pytest.mark.timeout(120)
 def test_tcgen05_attention_second_key_block_dominates():
-    """attention_tc2 keeps block 0's reference maximum for block 1 unless block 1 towers over it by more
-    than 2^8; this input (keys >= 128 scaled up) forces the redo path, plus rows where it is not taken."""
+    """Scores whose maximum sits far into the row (keys >= 128 scaled up): a guard for any softmax
+    variant that processes the key columns in blocks with a running reference maximum."""
     import torch
     from clip_retrieval_b200._lib import lib, check
 

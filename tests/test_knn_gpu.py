@@ -217,3 +217,26 @@ def test_tensor_scan_matches_oracle_and_fma_scan(b200, nq, k, n, d):
     assert ok, msg
     np.testing.assert_allclose(D, Df, atol=TOL)
     assert (I == If).mean() > 0.995         # ids agree except across near-ties
+
+
+def test_range_search_matches_oracle(b200):
+    """index.range_search (clip_filter.py:52): ids identical to the oracle except for rows whose exact
+    score lies within TOL of the threshold."""
+    d, n = 768, 30000
+    X = synth_ref.rows_f16(n, d)
+    Q = _queries(3, d)
+    idx = b200.B200FlatIndex(d)
+    idx.add(X)
+    S64 = knn_ref.scores_f64(X, Q)
+    for thr in (0.08, 0.02, 0.5):   # few hits, thousands of hits (buffer regrowth), none
+        lims, D, I = idx.range_search(Q, thr)
+        lo, Do, Io = knn_ref.range_search(X, Q, thr)
+        assert lims.dtype == np.uint64 and lims.shape == (4,)
+        for q in range(3):
+            got = set(I[lims[q]:lims[q + 1]].tolist())
+            ref = set(Io[lo[q]:lo[q + 1]].tolist())
+            for i in got ^ ref:
+                assert abs(S64[q, i] - thr) <= TOL, "id %d differs and is not at the threshold" % i
+            ids = I[lims[q]:lims[q + 1]]
+            assert np.all(np.diff(ids) > 0)
+            np.testing.assert_allclose(D[lims[q]:lims[q + 1]], S64[q, ids], atol=TOL)
