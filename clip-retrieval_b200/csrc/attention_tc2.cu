@@ -214,11 +214,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
-        // Both passes read the scores chunk by chunk (32 columns) with the NEXT chunk's tcgen05.ld already
-        // in flight while the current one is processed (two register buffers), so the TMEM latency is
-        // off the critical path and only its bandwidth remains.
-        auto chunk_max = [&](const uint32_t (&v)[32], int c, float& mm) {
-          const int lim = kmax - c * 32;   // columns j <= lim are visible
+        // pass 1: row maximum
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
+#pragma unroll 1
+        for (int c = 0; c < chunks; c++) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+          ptx::tmem_ld_wait();
+          const int lim = kmax - c * 32;
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -227,28 +232,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
             m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
             m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
           }
-          mm = fmaxf(mm, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        };
-        // pass 1: row maximum
-        float m = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
-        uint32_t va[32], vb[32];
-        ptx::tmem_ld_32x32b_x32(tbase, va);
-        ptx::tmem_ld_wait();
-#pragma unroll 1
-        for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
-          chunk_max(va, c, m);
-          ptx::tmem_ld_wait();
-          if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
-          if (c + 1 < chunks) chunk_max(vb, c + 1, m);
-          ptx::tmem_ld_wait();
+          m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         }
         // pass 2: exponentials, row sum, P -> swizzled K-major tile of this group
         const float mb = m * scale_log2e;
         float l0 = 0.f, l1 = 0.f;
-        auto chunk_exp = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll 1
+        for (int c = 0; c < chunks; c++) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+          ptx::tmem_ld_wait();
           const int lim = kmax - c * 32;
           uint32_t pk[16];
 #pragma unroll
@@ -268,17 +261,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
             const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
             *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
           }
-        };
-        ptx::tmem_ld_32x32b_x32(tbase, va);
-        ptx::tmem_ld_wait();
-#pragma unroll 1
-        for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
-          chunk_exp(va, c);
-          ptx::tmem_ld_wait();
-          if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
-          if (c + 1 < chunks) chunk_exp(vb, c + 1);
-          ptx::tmem_ld_wait();
         }
         float pe[8];
 #pragma unroll

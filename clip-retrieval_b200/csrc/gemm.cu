@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include <mutex>
+#include <cstdlib>
 #include <algorithm>
 
 namespace b200 {
@@ -128,6 +129,24 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   ep.out = (__nv_bfloat16*)d_C;
   ep.out_ld = N;
   ep.act = act;
+  // B200_GEMM_DEBUG=1: print where the MMA issuer of the pair kernel waits (bring-up aid; syncs the stream)
+  static const bool dbg_on = getenv("B200_GEMM_DEBUG") != nullptr;
+  if (dbg_on && bn == GEMM_MODE_PAIR) {
+    unsigned long long* d = nullptr;
+    B200_CUDA(cudaMalloc((void**)&d, 32));
+    B200_CUDA(cudaMemsetAsync(d, 0, 32, (cudaStream_t)stream));
+    ep.dbg = d;
+    int rc = gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    B200_CUDA(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    const double pairs = sms / 2;
+    fprintf(stderr, "[gemm dbg] M=%d N=%d K=%d act=%d res=%d: issuer cycles/pair %.0f, wait operands %.1f%%, wait accumulator %.1f%%, producer wait-for-slot %.1f%%\n",
+            M, N, K, act, d_residual != nullptr, h[2] / pairs, 100.0 * h[0] / (double)h[2], 100.0 * h[1] / (double)h[2],
+            100.0 * h[3] / (double)h[2]);
+    return rc;
+  }
   return gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream);
 }
 

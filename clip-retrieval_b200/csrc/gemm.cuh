@@ -45,6 +45,8 @@ struct GemmEpilogue {
   // Optional transposed store of the V third of a QKV projection (columns >= vt_col0): element
   // (row = b*T + t, col = vt_col0 + h*hd + dd) goes to vt[((b*heads + h)*hd + dd) * vt_Tp + t], i.e. V^T
   // per (sample, head) with keys contiguous — the K-major B operand of the P.V MMA (attention_tc.cu).
+  unsigned long long* dbg = nullptr;   // optional: [0] cycles the MMA issuer waited for operands, [1] for a free
+                                       // accumulator, [2] total issuer cycles, [3] producer waits for a free slot (pair kernel)
   __nv_bfloat16* vt = nullptr;
   int vt_col0 = 0, vt_T = 1, vt_Tp = 0, vt_hd = 64, vt_heads = 1;
 };

@@ -90,7 +90,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         }
         for (int kbi = 0; kbi < kb; kbi++) {
           if (m_nxt >= 0) ptx::tma_prefetch_2d(&tmA, kbi * GEMM_BK, m_nxt * G2_BM + (int)rank * 128);
+          const long long t0 = (ep.dbg && leader) ? clock64() : 0;
           ptx::mbar_wait(&empty[stage], phase ^ 1);
+          if (ep.dbg && leader) atomicAdd(ep.dbg + 3, (unsigned long long)(clock64() - t0));
           ptx::tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, &full[stage], kbi * GEMM_BK,
                                 m_blk * G2_BM + (int)rank * 128);
           ptx::tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, &full[stage], kbi * GEMM_BK,
@@ -111,12 +113,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_full = 0, w_acc = 0;
+      const long long t_begin = ep.dbg ? clock64() : 0;
       for (int tile = pair; tile < tiles; tile += npairs) {
+        long long t0 = ep.dbg ? clock64() : 0;
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        if (ep.dbg) w_acc += clock64() - t0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * G2_BN;
         for (int kbi = 0; kbi < kb; kbi++) {
+          t0 = ep.dbg ? clock64() : 0;
           ptx::mbar_wait(&full[stage], phase);
+          if (ep.dbg) w_full += clock64() - t0;
           ptx::tc_fence_after();
           const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + stage * G2_A_BYTES));
           const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sB + stage * G2_B_BYTES));
@@ -129,6 +137,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         ptx::umma_commit_pair(&tfull[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if (ep.dbg) {
+        atomicAdd(ep.dbg + 0, (unsigned long long)w_full);
+        atomicAdd(ep.dbg + 1, (unsigned long long)w_acc);
+        atomicAdd(ep.dbg + 2, (unsigned long long)(clock64() - t_begin));
       }
     }
     __syncwarp();
