@@ -19,7 +19,7 @@ namespace b200 {
 
 constexpr int G2_BM = 256;          // rows per pair tile (128 per CTA)
 constexpr int G2_BN = 256;
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 6;   // 7 stages (224 KB) measured no better: the issuer waits for operands ~20-28% either way
 constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;   // 16 KB (half of the 256-wide B tile)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
