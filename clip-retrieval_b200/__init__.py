@@ -11,11 +11,12 @@ from ._lib import lib, B200Error, library_path, launch_count  # noqa: F401
 from .index import B200FlatIndex, B200IVFFlatIndex, SynthSpec, load_index, merge_shard_results  # noqa: F401
 
 from .model import B200Clip, ClipArch, Tower, ARCHS, load_clip, synthetic_state_dict, convert_hf_state_dict  # noqa: F401,E402
+from .preprocess import B200Preprocess, to_rgb8  # noqa: F401,E402
 from .mapper import ClipMapper  # noqa: F401,E402
 from .sharded import ShardedIndex, shard_range  # noqa: F401,E402
 
 __all__ = [
-    "B200Clip", "ClipArch", "Tower", "ARCHS", "load_clip", "synthetic_state_dict", "convert_hf_state_dict", "ClipMapper", "ShardedIndex", "shard_range",
+    "B200Clip", "ClipArch", "Tower", "ARCHS", "load_clip", "synthetic_state_dict", "convert_hf_state_dict", "ClipMapper", "B200Preprocess", "to_rgb8", "ShardedIndex", "shard_range",
     "lib", "B200Error", "library_path", "launch_count",
     "B200FlatIndex", "B200IVFFlatIndex", "SynthSpec", "load_index", "merge_shard_results",
 ]

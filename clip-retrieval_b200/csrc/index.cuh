@@ -15,6 +15,12 @@ struct b200_index {
   int64_t id_base = 0;
   bool use_staged = true;   // FMA scan through the cp.async.bulk shared-memory ring (knn_scan.cu)
   bool use_mma = true;      // batched queries go through the tcgen05 scan (knn_mma.cu)
+  bool use_hi_only = true;  // > 128 queries: approximate hi-only pass + exact re-score + proof (knn_mma.cu)
+  int last_hi_only_fallbacks = 0;   // queries of the last batched search whose proof failed (re-run split)
+  const __half* norm_rows[2] = {nullptr, nullptr};   // cache of max_row ||x||^2 per scanned table
+  int64_t norm_n[2] = {0, 0};
+  float* norm_bound[2] = {nullptr, nullptr};
+  int norm_next = 0;
 
   // IVF-Flat
   int nlist = 0;            // 0 = flat
@@ -29,8 +35,8 @@ struct b200_index {
   int64_t max_list = 0;
 
   // scratch
-  void* ws[4] = {nullptr, nullptr, nullptr, nullptr};   // slot 0: scan internals; 1..3: callers
-  size_t ws_bytes[4] = {0, 0, 0, 0};
+  void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0: scan internals; 1..3: callers; 4,5: hi-only mode
+  size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
   std::mutex mu;
 
   // scan timing (CUDA events on the launching stream)

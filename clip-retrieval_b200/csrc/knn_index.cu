@@ -196,8 +196,10 @@ int b200_index_destroy(b200_index* idx) {
   DeviceGuard g(idx->device);
   cudaDeviceSynchronize();
   if (idx->rows) cudaFree(idx->rows);
-  for (int i = 0; i < 4; i++)
-    if (idx->ws[i]) cudaFree(idx->ws[i]);
+  for (void* w : idx->ws)
+    if (w) cudaFree(w);
+  for (float* b : idx->norm_bound)
+    if (b) cudaFree(b);
   for (auto e : idx->ev) cudaEventDestroy(e);
   ivf_free(idx);
   delete idx;
@@ -312,8 +314,11 @@ int b200_index_set_tensor_scan(b200_index* idx, int on) {
   B200_CHECK(idx, B200_ERR_INVALID, "set_tensor_scan: null index");
   idx->use_mma = (on & 1) != 0;
   idx->use_staged = (on & 4) == 0;  // bit 2 set: also disable the cp.async.bulk ring (A/B)
+  idx->use_hi_only = (on & 8) == 0; // bit 3 set: always the hi/lo split mode (no approximate pass)
   return B200_OK;
 }
+
+int b200_index_last_hi_only_fallbacks(const b200_index* idx) { return idx ? idx->last_hi_only_fallbacks : -1; }
 
 int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids) {
   B200_CHECK(idx && h_sizes, B200_ERR_INVALID, "ivf_lists: null argument");

@@ -177,8 +177,13 @@ class _IndexBase:
         return (D, I, R) if reconstruct else (D, I)
 
     def set_tensor_scan(self, on):
-        """Batched queries use the tcgen05 scan by default; False forces the FMA scan."""
-        check(lib.b200_index_set_tensor_scan(self._h, 1 if on else 0), "set_tensor_scan")
+        """Batched queries use the tcgen05 scan by default; False forces the FMA scan.  An int is passed
+        through as the C ABI's bit flags (1 tcgen05 scan, 4 no bulk-copy ring, 8 split mode only)."""
+        flags = (1 if on else 0) if isinstance(on, bool) else int(on)
+        check(lib.b200_index_set_tensor_scan(self._h, flags), "set_tensor_scan")
+
+    def last_hi_only_fallbacks(self):
+        return int(lib.b200_index_last_hi_only_fallbacks(self._h))
 
     def last_scan_ms(self):
         ms = C.c_float(0)

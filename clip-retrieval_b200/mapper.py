@@ -6,8 +6,14 @@ carries `image_tensor` fp32 [B,3,S,S], `text_tokens` int [B,77], `image_filename
 `metadata`, with embeddings as np.float16 [B, D] arrays owned by Python (the writer keeps them
 until flush: writer.py:43-56).  H2D copy, forward, L2-normalise, fp16 cast and D2H copy happen
 inside one C-ABI call per modality (b200_clip_encode_image / b200_clip_encode_text).
+
+Extension: when the batch carries `image_rgb8` (a list of decoded uint8 HWC
+images of any size — what a reader yields if its `preprocess` is `to_rgb8` instead of the torchvision
+transform) instead of `image_tensor`, Resize/CenterCrop/ToTensor/Normalize run on the GPU
+(`B200Preprocess`, bit-exact with the host transform) and feed the image tower in place.
 """
 from .model import load_clip
+from .preprocess import B200Preprocess
 
 
 class ClipMapper:
@@ -44,6 +50,7 @@ class ClipMapper:
         self.model = model
         self.model_img = model.encode_image
         self.model_txt = model.encode_text
+        self._gpu_preprocess = None
 
     def __call__(self, item):
         image_embs = None
@@ -52,7 +59,12 @@ class ClipMapper:
         text = None
         metadata = None
         if self.enable_image:
-            image_embs = self.model.embed_image(item["image_tensor"])
+            if "image_tensor" not in item and "image_rgb8" in item:
+                if self._gpu_preprocess is None:
+                    self._gpu_preprocess = B200Preprocess(self.model.arch.image_size)
+                image_embs = self.model.embed_image(self._gpu_preprocess(item["image_rgb8"]))
+            else:
+                image_embs = self.model.embed_image(item["image_tensor"])
             image_filename = item["image_filename"]
         if self.enable_text:
             text_embs = self.model.embed_text(item["text_tokens"])

@@ -100,8 +100,13 @@ int b200_index_set_id_base(b200_index* idx, int64_t id_base);
 int b200_index_set_nprobe(b200_index* idx, int nprobe);
 int b200_index_get_nprobe(const b200_index* idx);
 /* Batched queries (nq > 4, k <= 128) go through the tcgen05 scan by default; 0 forces the FMA scan
- * (kept for A/B measurements and parity tests between the two paths). */
+ * (kept for A/B measurements and parity tests between the paths).  Bit flags: 1 = tcgen05 scan on,
+ * 4 = FMA scan without the bulk-copy ring, 8 = tcgen05 scan always in hi/lo split mode (no
+ * approximate hi-only pass + exact re-score for nq > 128). */
 int b200_index_set_tensor_scan(b200_index* idx, int on);
+/* Queries of the last batched search whose exactness proof failed in hi-only mode and were re-run
+ * in split mode (0 in the common case; diagnostic). */
+int b200_index_last_hi_only_fallbacks(const b200_index* idx);
 /* IVF introspection used by ivf_metadata_ordering.get_old_to_new_mapping
  * (ivf_metadata_ordering.py:46-64): sizes[nlist] and, list after list, the ids in list order. */
 int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
@@ -209,6 +214,21 @@ int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int
  * ([B*heads*64, Tp] bf16, keys contiguous, columns >= T zero) — the layout the QKV GEMM epilogue writes. */
 int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads,
                                   int w, int causal, int device, void* stream);
+
+/* ---- image transform in front of the embed path ----------------------------
+ * Replaces `preprocess(PIL.Image)` as the reference calls it per image on the host
+ * (clip_retrieval/clip_inference/reader.py:98-106,158-165; the object `load_clip` returns,
+ * mapper.py:36-41): torchvision Resize(n_px, BICUBIC) -> CenterCrop(n_px) -> ToTensor ->
+ * Normalize(mean, std), bit-exact with Pillow's 8-bit resampler and torchvision's float32 ops.
+ * Input: n decoded images, RGB uint8 HWC, packed in one buffer (host or device) at byte offsets
+ * h_offsets[i] with sizes h_heights[i] x h_widths[i] (host arrays).  Output: float32
+ * [n, 3, n_px, n_px] on the device — the `image_tensor` layout `b200_clip_encode_image_device`
+ * takes.  One batch at a time per handle; returns after the batch has been produced on `stream`. */
+typedef struct b200_preproc b200_preproc;
+int b200_preproc_create(int n_px, const float* mean3, const float* std3, int device, b200_preproc** out);
+int b200_preproc_destroy(b200_preproc* p);
+int b200_preproc_run(b200_preproc* p, const uint8_t* pixels, int pixels_on_device, const int64_t* h_offsets,
+                     const int32_t* h_heights, const int32_t* h_widths, int n, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

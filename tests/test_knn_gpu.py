@@ -219,6 +219,51 @@ def test_tensor_scan_matches_oracle_and_fma_scan(b200, nq, k, n, d):
     assert (I == If).mean() > 0.995         # ids agree except across near-ties
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("nq,k,n,d", [(129, 40, 50021, 768), (300, 40, 200000, 768), (1000, 10, 150000, 512),
+                                      (257, 64, 33000, 1024)])
+def test_hi_only_scan_is_exact(b200, nq, k, n, d):
+    """More than 128 queries: approximate hi-only tcgen05 pass + exact re-score + per-query proof
+    (knn_mma.cu).  Must equal the float64 ranking and the split-mode scan of the same index."""
+    X = synth_ref.rows_f16(n, d)
+    Q = _queries(nq, d)
+    idx = b200.B200FlatIndex(d)
+    idx.add(X)
+    S64 = knn_ref.scores_f64(X, Q)
+    D, I = idx.search(Q, k)
+    ok, msg, _ = knn_ref.check_topk(D, I, S64, k, tol=TOL)
+    assert ok, msg
+    assert idx.last_hi_only_fallbacks() == 0            # iid rows: every proof succeeds
+    idx.set_tensor_scan(1 | 8)                          # split mode only
+    Ds, Is = idx.search(Q, k)
+    ok, msg, _ = knn_ref.check_topk(Ds, Is, S64, k, tol=TOL)
+    assert ok, msg
+    np.testing.assert_allclose(D, Ds, atol=TOL)
+    assert (I == Is).mean() > 0.995
+
+
+@pytest.mark.timeout(300)
+def test_hi_only_scan_falls_back_on_packed_duplicates(b200):
+    """Rows that are exact copies of each other tie inside the error bound of the approximate pass:
+    the proof must fail for the queries whose k-th neighbour sits in such a pack, those queries are
+    re-run in split mode, and the result (ties by ascending id) is still exact."""
+    d, k, nq = 768, 40, 200
+    base = synth_ref.rows_f16(5000, d)
+    X = np.concatenate([base, np.repeat(base[:40], 100, axis=0), base[::-1]])   # 100 copies of 40 rows + a mirrored copy
+    Q = _queries(nq, d)
+    Q[:8] = 0.25 * base[:8].astype(np.float32) + 1e-3 * Q[:8]   # queries that land on the packed rows
+    idx = b200.B200FlatIndex(d)
+    idx.add(X)
+    D, I = idx.search(Q, k)
+    ok, msg, _ = knn_ref.check_topk(D, I, knn_ref.scores_f64(X, Q), k, tol=TOL)
+    assert ok, msg
+    assert idx.last_hi_only_fallbacks() >= 8
+    idx.set_tensor_scan(False)
+    Df, If = idx.search(Q, k)
+    assert np.array_equal(I[:8], If[:8])                # exact ties: ascending ids in both paths
+    np.testing.assert_allclose(D, Df, atol=TOL)
+
+
 def test_range_search_matches_oracle(b200):
     """index.range_search (clip_filter.py:52): ids identical to the oracle except for rows whose exact
     score lies within TOL of the threshold."""
