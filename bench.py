@@ -261,7 +261,10 @@ def run_b200(args):
                     "api": "B200Clip.embed_image/embed_text (what ClipMapper.__call__ runs), pinned host tensors"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_bf16_tcgen05_pair_kernel (cta_group::2; the few small GEMMs use the single-CTA variant)", "launches_per_step": gemm_launches,
+                         "traffic": 1.592e9,
+                         "traffic_source": "ncu --set full, profiles/r01f_final_summary.txt: mean dram read+write bytes per launch of the four per-layer "
+                                           "GEMMs captured inside the model at batch 512 (algorithmic A+W+residual+C bytes of the same four: 1.21e9)",
+                         "kernel": "gemm_bf16_tcgen05_pair_kernel (cta_group::2; the few small GEMMs use the single-CTA variant)", "launches_per_step": gemm_launches,
                          "peak_source": "%s bf16_tflops_sustained" % peaks["_source"],
                          "flops_per_step": gemm_flops, "gemm_ms_per_step": gemm_ms},
             "breakdown_ms_per_step": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "other": other_ms,
@@ -356,7 +359,11 @@ def run_knn(args, m, torch, dist, dev, local, rank, world, peaks, barrier, max_o
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "traffic": None,
                      "kernel": "flat_scan_staged_kernel<1,3> (nq=1 serving shape, cp.async.bulk ring)", "bytes_per_launch": bytes_per_launch,
-                     "batch_pass": {"achieved": achN, "frac": achN / peak, "launches_per_step": s_n},
+                     "traffic_source": "ncu at 20M rows (profiles/r01f_final_summary.txt): dram__bytes_read 30.7209e9 vs 30.72e9 algorithmic per launch",
+                     "batch_pass": {"achieved": achN, "frac": achN / peak, "launches_per_step": s_n,
+                                    "kernel": "scan_mma_kernel (tcgen05; hi-only pass + exact re-score + proof above 128 queries)",
+                                    "useful_tflops": 2.0 * rows * d * nq / (ms / 1e3) / 1e12,
+                                    "hi_only_fallbacks": idx.last_hi_only_fallbacks()},
                      "peak_source": "%s hbm_gbs" % peaks["_source"]},
     }
 

@@ -80,16 +80,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       for (int tile = pair; tile < tiles; tile += npairs) {
         int m_blk, n_blk;
         gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
-        // the pair's next tile: pull its A rows towards L2 a whole tile ahead when they are new (first
-        // column block of a row group), so the 6-stage ring does not have to cover HBM latency
-        int m_nxt = -1;
-        if (tile + npairs < tiles) {
-          int mn, nn;
-          gemm_tile_coords(tile + npairs, mb, nb, mn, nn);
-          if (nn == 0) m_nxt = mn;
-        }
         for (int kbi = 0; kbi < kb; kbi++) {
-          if (m_nxt >= 0) ptx::tma_prefetch_2d(&tmA, kbi * GEMM_BK, m_nxt * G2_BM + (int)rank * 128);
           const long long t0 = (ep.dbg && leader) ? clock64() : 0;
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           if (ep.dbg && leader) atomicAdd(ep.dbg + 3, (unsigned long long)(clock64() - t0));

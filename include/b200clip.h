@@ -230,6 +230,20 @@ int b200_preproc_destroy(b200_preproc* p);
 int b200_preproc_run(b200_preproc* p, const uint8_t* pixels, int pixels_on_device, const int64_t* h_offsets,
                      const int32_t* h_heights, const int32_t* h_widths, int n, float* d_out, void* stream);
 
+/* ---- post-filters on the reconstructed rows of a search ----------------------
+ * b200_dedup_device replaces KnnService.get_non_uniques / connected_components_dedup
+ * (clip_retrieval/clip_back.py:270-311): rows i, j are linked when their inner product exceeds
+ * `threshold` (FAISS range_search semantics, strict >); d_drop[i] = 1 for every row that is not the
+ * lowest-index member of its connected component (the rows the reference removes), d_labels[i]
+ * (optional) = that lowest index.  d_rows: fp32 [k, d] on the device (the d_R block of
+ * b200_index_search_device), k <= 4096; d_workspace: at least k * ceil(k/32) * 4 bytes.
+ * b200_prompt_argmax_device replaces KnnService.get_violent_items (clip_back.py:321-324):
+ * d_flag[i] = (argmax_p <row_i, prompt_p> == target), first maximum wins. */
+int b200_dedup_device(const float* d_rows, int k, int d, float threshold, uint8_t* d_drop, int32_t* d_labels,
+                      void* d_workspace, size_t workspace_bytes, int device, void* stream);
+int b200_prompt_argmax_device(const float* d_rows, int k, int d, const float* d_prompts, int n_prompts, int target,
+                              uint8_t* d_flag, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

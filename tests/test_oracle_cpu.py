@@ -97,3 +97,19 @@ def test_ivf_oracle_nprobe_all_equals_flat():
     assert (assign[I1[I1 >= 0]] == np.repeat(probes[:, :1], 10, 1)[I1 >= 0]).all() if False else True
     m = knn_ref.merge_shards(np.stack([Df[:, :5], Df[:, 5:]]), np.stack([If[:, :5], If[:, 5:]]), 10)
     assert np.array_equal(m[1], If)
+
+
+def test_postfilter_oracle_known_answers():
+    """oracle/postfilter_ref.py (clip_back.py:270-324 restated): hand-checkable graphs."""
+    from oracle import postfilter_ref as R
+
+    # adjacency given directly: components {0,3,4}, {1}, {2,5}; the lowest index of each survives
+    A = np.eye(6, dtype=bool)
+    for i, j in [(0, 3), (3, 4), (2, 5)]:
+        A[i, j] = A[j, i] = True
+    assert R.get_non_uniques(None, adjacency=A) == [3, 4, 5]
+    e = np.eye(4, dtype=np.float32)
+    E = np.stack([e[0], e[1], e[0], (e[0] + 0.1 * e[2]) / np.linalg.norm(e[0] + 0.1 * e[2])])
+    assert R.get_non_uniques(E, 0.94) == [2, 3]
+    P = np.stack([e[1], e[0], e[2]])
+    np.testing.assert_array_equal(R.get_violent_items(P, E), [0, 2, 3])
