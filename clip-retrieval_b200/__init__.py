@@ -8,7 +8,7 @@ Everything numeric runs in the CUDA library `lib/libb200clip.so` (C ABI in inclu
 there is no CPU fallback: importing works without a GPU, calling compute without one raises.
 """
 from ._lib import lib, B200Error, library_path, launch_count  # noqa: F401
-from .index import B200FlatIndex, B200IVFFlatIndex, SynthSpec, load_index, merge_shard_results  # noqa: F401
+from .index import B200FlatIndex, B200IVFFlatIndex, SynthSpec, load_index, merge_shard_results, train_kmeans, build_ivf_index  # noqa: F401
 
 from .model import B200Clip, ClipArch, Tower, ARCHS, load_clip, synthetic_state_dict, convert_hf_state_dict  # noqa: F401,E402
 from .preprocess import B200Preprocess, to_rgb8  # noqa: F401,E402
@@ -19,5 +19,5 @@ from .sharded import ShardedIndex, shard_range  # noqa: F401,E402
 __all__ = [
     "B200Clip", "ClipArch", "Tower", "ARCHS", "load_clip", "synthetic_state_dict", "convert_hf_state_dict", "ClipMapper", "get_non_uniques", "get_violent_items", "dedup_mask", "B200Preprocess", "to_rgb8", "ShardedIndex", "shard_range",
     "lib", "B200Error", "library_path", "launch_count",
-    "B200FlatIndex", "B200IVFFlatIndex", "SynthSpec", "load_index", "merge_shard_results",
+    "B200FlatIndex", "B200IVFFlatIndex", "SynthSpec", "load_index", "merge_shard_results", "train_kmeans", "build_ivf_index",
 ]

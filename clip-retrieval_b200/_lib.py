@@ -111,6 +111,7 @@ PROTOTYPES = {
     "b200_gemm_set_pair_mode": (_i, [_i]),
     "b200_gemm_bf16_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_index_last_hi_only_fallbacks": (_i, [_vp]),
+    "b200_kmeans_train_f16": (_i, [_vp, _i64, _i, _i, _i, C.c_uint64, _i, _vp, _vp, _i]),
     "b200_dedup_device": (_i, [_vp, _i, _i, C.c_float, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "b200_prompt_argmax_device": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "b200_preproc_create": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, C.POINTER(_vp)]),

@@ -476,3 +476,175 @@ int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned l
 }
 
 }  // namespace b200
+
+// ---- k-means training of the coarse quantiser -----------------------------------
+// The GPU counterpart of the training step behind `clip-retrieval index` (clip_index.py:12-31 ->
+// autofaiss.build_index -> faiss Clustering): Lloyd iterations under the index's own assignment rule
+// (centroid of maximum inner product, ties to the lower list id, centroids rounded to fp16 exactly as
+// b200_index_create_ivfflat stores them), centroid = mean of its rows, FAISS-style split of empty
+// clusters.  Assignment reuses ivf_assign_kernel; the update is a deterministic segmented sum: rows
+// are radix-sorted by list (stable, so ascending row id inside a list) and one CTA per list adds them
+// in that order, thread = column — the same rows always give the same centroids.
+namespace b200 {
+
+__global__ void kmeans_gather_kernel(const __half* __restrict__ X, int d, const int64_t* __restrict__ pick, int nlist,
+                                     float* __restrict__ C32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nlist * d) return;
+  const int l = (int)(i / d), j = (int)(i - (int64_t)l * d);
+  C32[i] = __half2float(X[pick[l] * d + j]);
+}
+
+__global__ void kmeans_to_half_kernel(const float* __restrict__ C32, int64_t count, __half* __restrict__ C16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) C16[i] = __float2half_rn(C32[i]);
+}
+
+// block = list; thread = column (strided); rows of the list in ascending row id.
+__global__ void __launch_bounds__(256)
+kmeans_update_kernel(const __half* __restrict__ X, int d, const uint32_t* __restrict__ sorted_src,
+                     const int64_t* __restrict__ offsets, float* __restrict__ C32, int spherical) {
+  const int l = blockIdx.x;
+  const int64_t p0 = offsets[l], p1 = offsets[l + 1];
+  if (p1 == p0) return;   // empty: handled by the split step
+  const float inv = 1.0f / (float)(p1 - p0);
+  __shared__ float s_part[256];
+  float n2 = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float s = 0.f;
+    for (int64_t p = p0; p < p1; p++) s += __half2float(X[(int64_t)sorted_src[p] * d + j]);
+    const float m = s * inv;
+    C32[(int64_t)l * d + j] = m;
+    n2 = fmaf(m, m, n2);
+  }
+  if (!spherical) return;
+  s_part[threadIdx.x] = n2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float nrm = sqrtf(s_part[0]);
+  if (nrm > 0.f)
+    for (int j = threadIdx.x; j < d; j += blockDim.x) C32[(int64_t)l * d + j] /= nrm;
+}
+
+// FAISS Clustering::split_clusters, made deterministic: the empty list `ci` takes the centroid of `cj`
+// and the two are perturbed symmetrically (1 +- 1/1024, alternating by column).
+__global__ void kmeans_split_kernel(float* __restrict__ C32, int d, int ci, int cj) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const float eps = 1.0f / 1024.0f;
+  const float v = C32[(int64_t)cj * d + j];
+  if (j % 2 == 0) {
+    C32[(int64_t)ci * d + j] = v * (1.0f + eps);
+    C32[(int64_t)cj * d + j] = v * (1.0f - eps);
+  } else {
+    C32[(int64_t)ci * d + j] = v * (1.0f - eps);
+    C32[(int64_t)cj * d + j] = v * (1.0f + eps);
+  }
+}
+
+__global__ void iota_u32_kernel(uint32_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
+static inline uint64_t kmeans_mix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+}  // namespace b200
+
+extern "C" int b200_kmeans_train_f16(const void* d_rows, int64_t n, int d, int nlist, int niter, uint64_t seed,
+                                     int spherical, float* h_centroids, int64_t* h_sizes, int device) {
+  using namespace b200;
+  B200_CHECK(d_rows && h_centroids, B200_ERR_INVALID, "kmeans_train: null argument");
+  B200_CHECK(d >= 8 && d % 8 == 0 && d <= 2048, B200_ERR_INVALID, "kmeans_train: d=%d (multiple of 8, <= 2048)", d);
+  B200_CHECK(nlist >= 1 && n >= nlist && n < (1ll << 31) && niter >= 0, B200_ERR_INVALID,
+             "kmeans_train: n=%lld nlist=%d niter=%d (need nlist <= n < 2^31)", (long long)n, nlist, niter);
+  DeviceGuard g(device);
+  const __half* X = (const __half*)d_rows;
+  const int cpr = d / 8;
+  const size_t count = (size_t)nlist * d;
+  float* C32 = nullptr; __half* C16 = nullptr; int64_t* d_pick = nullptr; int64_t* d_off = nullptr;
+  uint32_t *assign = nullptr, *src = nullptr, *assign2 = nullptr, *src2 = nullptr;
+  void* tmp = nullptr;
+  std::vector<void*> frees;
+  auto cleanup = [&]() { for (void* p : frees) cudaFree(p); };
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    B200_CUDA(cudaMalloc(p, bytes));
+    frees.push_back(*p);
+    return B200_OK;
+  };
+  int rc = [&]() -> int {
+    B200_TRY(alloc((void**)&C32, count * 4));
+    B200_TRY(alloc((void**)&C16, count * 2));
+    B200_TRY(alloc((void**)&d_pick, (size_t)nlist * 8));
+    B200_TRY(alloc((void**)&d_off, (size_t)(nlist + 1) * 8));
+    B200_TRY(alloc((void**)&assign, (size_t)n * 4));
+    B200_TRY(alloc((void**)&src, (size_t)n * 4));
+    B200_TRY(alloc((void**)&assign2, (size_t)n * 4));
+    B200_TRY(alloc((void**)&src2, (size_t)n * 4));
+    // initial centroids: one seeded pick inside each of nlist equal strides of the rows (all distinct)
+    std::vector<int64_t> pick(nlist);
+    for (int i = 0; i < nlist; i++) {
+      const int64_t lo = (int64_t)(((__int128)i * n) / nlist), hi = (int64_t)(((__int128)(i + 1) * n) / nlist);
+      const uint64_t span = (uint64_t)std::max<int64_t>(1, hi - lo);
+      pick[i] = lo + (int64_t)(kmeans_mix(seed ^ ((uint64_t)i * 0xD1342543DE82EF95ull)) % span);
+    }
+    B200_CUDA(cudaMemcpy(d_pick, pick.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice));
+    kmeans_gather_kernel<<<(unsigned)((count + 255) / 256), 256>>>(X, d, d_pick, nlist, C32);
+    B200_LAUNCH_OK();
+    int bits = 1;
+    while ((1ll << bits) < nlist) bits++;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, assign, assign2, src, src2, (int)n, 0, bits);
+    B200_TRY(alloc(&tmp, tmp_bytes));
+    ivf_assign_fn afn = pick_ivf_assign((cpr + 31) / 32);
+    B200_CHECK(afn != nullptr, B200_ERR_UNSUPPORTED, "kmeans_train: d=%d", d);
+    std::vector<int64_t> off(nlist + 1);
+    for (int it = 0; it <= niter; it++) {
+      // assignment under the fp16-rounded centroids (the rule the index itself applies on add)
+      kmeans_to_half_kernel<<<(unsigned)((count + 255) / 256), 256>>>(C32, (int64_t)count, C16);
+      B200_LAUNCH_OK();
+      afn<<<(unsigned)((n + 7) / 8), 256>>>(reinterpret_cast<const uint4*>(X), n, cpr, reinterpret_cast<const uint4*>(C16),
+                                            nlist, assign);
+      B200_LAUNCH_OK();
+      iota_u32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, n);
+      B200_LAUNCH_OK();
+      cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, assign, assign2, src, src2, (int)n, 0, bits);
+      count_launch(4);
+      offsets_from_sorted_kernel<<<(nlist + 1 + 255) / 256, 256>>>(assign2, n, nlist, d_off);
+      B200_LAUNCH_OK();
+      B200_CUDA(cudaMemcpy(off.data(), d_off, (size_t)(nlist + 1) * 8, cudaMemcpyDeviceToHost));
+      if (it == niter) break;   // the last round only refreshes the sizes of the final centroids
+      kmeans_update_kernel<<<nlist, 256>>>(X, d, src2, d_off, C32, spherical);
+      B200_LAUNCH_OK();
+      // empty clusters: split the (currently) largest one, ties to the lower id; sizes halve as in FAISS
+      std::vector<int64_t> sz(nlist);
+      for (int l = 0; l < nlist; l++) sz[l] = off[l + 1] - off[l];
+      for (int ci = 0; ci < nlist; ci++) {
+        if (sz[ci] != 0) continue;
+        int cj = 0;
+        for (int l = 1; l < nlist; l++)
+          if (sz[l] > sz[cj]) cj = l;
+        if (sz[cj] < 2) break;
+        kmeans_split_kernel<<<(d + 255) / 256, 256>>>(C32, d, ci, cj);
+        B200_LAUNCH_OK();
+        sz[ci] = sz[cj] / 2;
+        sz[cj] -= sz[ci];
+      }
+    }
+    B200_CUDA(cudaMemcpy(h_centroids, C32, count * 4, cudaMemcpyDeviceToHost));
+    if (h_sizes)
+      for (int l = 0; l < nlist; l++) h_sizes[l] = off[l + 1] - off[l];
+    return B200_OK;
+  }();
+  cudaDeviceSynchronize();
+  cleanup();
+  return rc;
+}

@@ -312,3 +312,34 @@ def merge_shard_results(Dg, Ig, k):
         "topk_merge",
     )
     return D, I
+
+
+def train_kmeans(rows, nlist, niter=10, seed=1234, spherical=False, device=0):
+    """IVF coarse-quantiser training on the GPU (C ABI `b200_kmeans_train_f16`): the counterpart of the
+    training step of `clip-retrieval index` (clip_index.py:12-31 -> autofaiss/faiss Clustering) over the
+    fp16 rows the writer produces.  rows: np.float16/float32 [n, d] or a CUDA half tensor.
+    Returns (centroids np.float32 [nlist, d], sizes np.int64 [nlist])."""
+    torch = _torch()
+    if _is_torch(rows):
+        t = rows.detach()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(rows))
+    dev = t.device if t.is_cuda else torch.device("cuda", device)
+    t = t.to(device=dev, dtype=torch.float16).contiguous()
+    n, d = t.shape
+    cent = np.empty((nlist, d), np.float32)
+    sizes = np.empty(nlist, np.int64)
+    check(lib.b200_kmeans_train_f16(C.c_void_p(t.data_ptr()), n, d, int(nlist), int(niter), C.c_uint64(seed),
+                                    1 if spherical else 0, C.c_void_p(cent.ctypes.data), C.c_void_p(sizes.ctypes.data),
+                                    dev.index or 0), "kmeans_train")
+    return cent, sizes
+
+
+def build_ivf_index(rows, nlist, niter=10, seed=1234, nprobe=1, device=0):
+    """train + create + add: an IVF-Flat index over `rows` (the GPU analogue of autofaiss.build_index
+    for an "IVF{nlist},Flat" key, clip_index.py:24-31)."""
+    cent, _ = train_kmeans(rows, nlist, niter=niter, seed=seed, device=device)
+    idx = B200IVFFlatIndex(cent.shape[1], nlist, cent, device=device)
+    idx.add(rows)
+    idx.nprobe = nprobe
+    return idx

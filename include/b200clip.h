@@ -230,6 +230,18 @@ int b200_preproc_destroy(b200_preproc* p);
 int b200_preproc_run(b200_preproc* p, const uint8_t* pixels, int pixels_on_device, const int64_t* h_offsets,
                      const int32_t* h_heights, const int32_t* h_widths, int n, float* d_out, void* stream);
 
+/* ---- IVF training --------------------------------------------------------------
+ * k-means for the coarse quantiser of b200_index_create_ivfflat: the GPU counterpart of the training
+ * step behind `clip-retrieval index` (clip_retrieval/clip_index.py:12-31 -> autofaiss.build_index ->
+ * faiss Clustering) on the fp16 rows the writer produces (writer.py:67-87).  `niter` Lloyd iterations
+ * from one seeded pick per stride of the rows; assignment = centroid of maximum inner product under
+ * fp16-rounded centroids (the index's own add rule, ties to the lower id); update = mean of the
+ * assigned rows (optionally L2-normalised: `spherical`); an empty cluster takes a perturbed copy of the
+ * largest one (FAISS split_clusters, chosen deterministically).  d_rows: fp16 [n, d] on the device;
+ * h_centroids: fp32 [nlist, d] on the host; h_sizes (optional): rows per list under the result. */
+int b200_kmeans_train_f16(const void* d_rows, int64_t n, int d, int nlist, int niter, uint64_t seed, int spherical,
+                          float* h_centroids, int64_t* h_sizes, int device);
+
 /* ---- post-filters on the reconstructed rows of a search ----------------------
  * b200_dedup_device replaces KnnService.get_non_uniques / connected_components_dedup
  * (clip_retrieval/clip_back.py:270-311): rows i, j are linked when their inner product exceeds
