@@ -12,10 +12,14 @@ pytestmark = pytest.mark.gpu
 
 
 def _blobs(n, d, nc, seed, spread=0.15):
+    """nc well-separated blobs, rows grouped blob after blob in equal shares: the trainer's one-pick-
+    per-stride initialisation then starts with one centroid inside every blob, so no row is ever near
+    a decision boundary and the device and the oracle must agree bit for bit."""
     rng = np.random.default_rng(seed)
     c = rng.standard_normal((nc, d)).astype(np.float32)
     c /= np.linalg.norm(c, axis=1, keepdims=True)
-    x = c[rng.integers(0, nc, n)] + spread * rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)
+    owner = (np.arange(n) * nc) // n
+    x = c[owner] + spread * rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     return x.astype(np.float16)
 
@@ -51,6 +55,7 @@ def test_build_ivf_index_from_trained_centroids():
     the lists the index builds are the ones the trainer reported."""
     n, d, nlist, k = 30000, 256, 32, 10
     X = _blobs(n, d, nlist, seed=5)
+    X = X[np.random.default_rng(0).permutation(n)]          # arbitrary order: lists of unequal sizes
     idx = b200.build_ivf_index(X, nlist, niter=4, seed=11, nprobe=nlist)
     cent, sizes = b200.train_kmeans(X, nlist, niter=4, seed=11)
     got_sizes, _ = idx.invlists()
