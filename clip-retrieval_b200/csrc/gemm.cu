@@ -120,9 +120,14 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   const int bn = gemm_pick_bn(M, N, sms);
   CUtensorMap tmA, tmB;
   B200_TRY(make_tmap_2d(&tmA, d_A, 1, (uint64_t)M, (uint64_t)K, (uint64_t)K, GEMM_BM, GEMM_BK));
-  B200_TRY(make_tmap_2d(&tmB, d_W, 1, (uint64_t)N, (uint64_t)K, (uint64_t)K, bn == GEMM_MODE_PAIR ? 128u : (uint32_t)bn,
-                        GEMM_BK));
+  // B200_GEMM_HALFB=1 (timing experiment, wrong numbers): each CTA of a pair loads only 64 of its 128 B rows,
+  // i.e. the operand traffic a 2-pair cluster with a multicast B tile would have (48 instead of 64 B/clk/SM).
+  static const bool half_b = getenv("B200_GEMM_HALFB") != nullptr;
+  const bool exp_half = half_b && bn == GEMM_MODE_PAIR;
+  B200_TRY(make_tmap_2d(&tmB, d_W, 1, (uint64_t)N, (uint64_t)K, (uint64_t)K,
+                        bn == GEMM_MODE_PAIR ? (exp_half ? 64u : 128u) : (uint32_t)bn, GEMM_BK));
   GemmEpilogue ep;
+  if (exp_half) ep.exp_b_bytes = 64 * GEMM_BK * 2;
   ep.bias = d_bias;
   ep.residual = (const __nv_bfloat16*)d_residual;
   ep.res_ld = N;

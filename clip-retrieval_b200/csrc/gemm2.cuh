@@ -90,7 +90,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                                 n_blk * G2_BN + (int)rank * 128);
           // The peer's loads complete on the leader's barrier too (peer bit cleared in the TMA); the peer
           // cannot run a ring cycle ahead because its empty[] is released by the leader's MMA commit.
-          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+          if (leader)
+            ptx::mbar_arrive_expect_tx(&full[stage], 2 * (G2_A_BYTES + (ep.exp_b_bytes ? ep.exp_b_bytes : G2_B_BYTES)));
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -52,7 +52,7 @@ constexpr int MS_BK = 64;
 constexpr int MS_STAGES = 6;
 constexpr int MS_CAP = 512;      // candidate buffer entries per (CTA, query)
 constexpr int MS_KMAX = 128;     // k supported by this path
-constexpr int MS_THREADS = 192;
+constexpr int MS_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int MS_A_BYTES = MS_BM * MS_BK * 2;
 constexpr int MS_B_BYTES = (MS_BN / 2) * MS_BK * 2;  // each CTA of the pair stages half of the Q' tile
 constexpr int MS_STAGE_BYTES = MS_A_BYTES + MS_B_BYTES;
@@ -284,7 +284,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       for (int a = 0; a < 2; a++) {
         ptx::mbar_init(&tfull[a], 1);
-        ptx::mbar_init(&tempty[a], 8);
+        ptx::mbar_init(&tempty[a], 16);   // 8 epilogue warps x 2 CTAs
       }
       ptx::fence_barrier_init();
     }
@@ -349,8 +349,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncwarp();
   } else {
     // ---------------- epilogue: thresholded append + compaction ----------------
-    const int q4 = warp & 3;
-    const int ew = warp - 2;  // 0..3
+    const int q4 = warp & 3;          // TMEM lane quarter this warp may read (warp id % 4)
+    const int ew = warp - 2;          // 0..7
+    const int half = ew >> 2;         // the two warps of a quarter take alternate 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     unsigned long long* my_cand = cand + (int64_t)blockIdx.x * groups * QG * MS_CAP;
@@ -364,13 +365,22 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t tbase = tmem_base + acc * MS_BN + ((uint32_t)(q4 * 32) << 16);
         const int gq = min(QG, nq - g * QG);   // live queries of this group
         const int nchunks = (gq + 31) / 32;
+        const int my_last = nchunks - 1 - ((nchunks - 1 - half) & 1);   // last chunk index of this warp (< half: none)
+        if (my_last < half) {   // nothing to read in this accumulator: release it right away
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&tempty[acc]);
+            else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
+          }
+        }
 #pragma unroll 1
-        for (int c = 0; c < nchunks; c++) {
+        for (int c = half; c < nchunks; c += 2) {
           uint32_t hi[32], lo[HILO ? 32 : 1];
           ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
           if constexpr (HILO) ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
           ptx::tmem_ld_wait();
-          if (c == nchunks - 1) {
+          if (c == my_last) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -417,8 +427,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (acc == 0) acc_phase ^= 1;
         // compaction of this group's buffers that could overflow during the next tile
         __threadfence_block();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int qq = ew; qq < gq; qq += 4) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int qq = ew; qq < gq; qq += 8) {
           const int q = g * QG + qq;
           const int cnt = s_cnt[q];
           if (cnt > MS_CAP - MS_BM) {
@@ -429,11 +439,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     // final pass: every (CTA, query) buffer reduced to its k best and written densely for the merge
-    for (int q = ew; q < nq; q += 4) {
+    for (int q = ew; q < nq; q += 8) {
       unsigned long long* buf = my_cand + (int64_t)q * MS_CAP;
       const int cnt = s_cnt[q];
       if (cnt > k) compact_buffer(buf, min(cnt, MS_CAP), k, lane);

@@ -1,0 +1,48 @@
+"""Sustained (power-capped) throughput of the model's four GEMM shapes with and without their epilogue
+features: each configuration runs back to back for ~1.5 s after a 1 s warm-up of the same kernel, so the
+clocks are the ones the model sees, not burst clocks."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from clip_retrieval_b200._lib import lib
+
+M = 1024 * 257
+st = torch.cuda.current_stream().cuda_stream
+
+
+def run(name, N, K, bias, res, act, secs=1.5):
+    A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda") if bias else None
+    R = torch.randn(M, N, device="cuda").bfloat16() if res else None
+    Cc = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+    def go():
+        lib.b200_gemm_bf16_device(A.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None, R.data_ptr() if res else None,
+                                  Cc.data_ptr(), M, N, K, act, 0, st)
+    t0 = time.time()
+    while time.time() - t0 < 1.0:
+        for _ in range(20):
+            go()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(20, int(secs / 0.0015))
+    e0.record()
+    for _ in range(reps):
+        go()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print("%-7s N=%d K=%d bias=%d res=%d act=%d: %.3f ms  %.0f TFLOP/s" % (name, N, K, bias, res, act, ms, 2.0 * M * N * K / ms / 1e9),
+          flush=True)
+
+
+for name, N, K, feats in (("qkv", 3072, 1024, [(0, 0, 0), (1, 0, 0)]),
+                          ("out", 1024, 1024, [(0, 0, 0), (1, 0, 0), (1, 1, 0)]),
+                          ("fc", 4096, 1024, [(0, 0, 0), (1, 0, 0), (1, 0, 1)]),
+                          ("c_proj", 1024, 4096, [(0, 0, 0), (1, 1, 0)])):
+    for bias, res, act in feats:
+        run(name, N, K, bias, res, act)
