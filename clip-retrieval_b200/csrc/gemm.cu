@@ -128,6 +128,8 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
                         bn == GEMM_MODE_PAIR ? (exp_half ? 64u : 128u) : (uint32_t)bn, GEMM_BK));
   GemmEpilogue ep;
   if (exp_half) ep.exp_b_bytes = 64 * GEMM_BK * 2;
+  static const bool no_ldtm = getenv("B200_GEMM_NOLDTM") != nullptr;   // timing experiment: epilogue without tcgen05.ld
+  if (no_ldtm && bn == GEMM_MODE_PAIR) ep.exp_skip_tmem = 1;
   ep.bias = d_bias;
   ep.residual = (const __nv_bfloat16*)d_residual;
   ep.res_ld = N;

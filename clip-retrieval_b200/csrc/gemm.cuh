@@ -48,6 +48,7 @@ struct GemmEpilogue {
   unsigned long long* dbg = nullptr;   // optional: [0] cycles the MMA issuer waited for operands, [1] for a free
                                        // accumulator, [2] total issuer cycles, [3] producer waits for a free slot (pair kernel)
   int exp_b_bytes = 0;                 // timing experiment only (B200_GEMM_HALFB): bytes of B each CTA really loads per stage
+  int exp_skip_tmem = 0;               // timing experiment only (B200_GEMM_NOLDTM): the epilogue does not read the accumulator
   __nv_bfloat16* vt = nullptr;
   int vt_col0 = 0, vt_T = 1, vt_Tp = 0, vt_hd = 64, vt_heads = 1;
 };

@@ -177,8 +177,13 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       for (int ci = 0; ci < CPW; ci++) {
         const int c = half * CPW + ci;
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
-        ptx::tmem_ld_wait();
+        if (!ep.exp_skip_tmem) {
+          ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = 0x3f800000u;
+        }
         if (ci == CPW - 1) {
           ptx::tc_fence_before();
           __syncwarp();

@@ -39,6 +39,7 @@
 #include "ptx.cuh"
 #include "gemm.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -244,7 +245,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MS_THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n, int d,
                 int nq, int groups, int k, unsigned long long* __restrict__ cand /* [grid][groups*128][CAP] */,
                 unsigned long long* __restrict__ dense /* [nq][grid][k] */, int tile_stride,
-                const float* __restrict__ thr_init /* [nq] lower bounds on the k-th best score, or null */) {
+                const float* __restrict__ thr_init /* [nq] lower bounds on the k-th best score, or null */,
+                int exp_mode /* timing experiments: 1 = read TMEM but skip the tests, 2 = read one chunk, test all */) {
   constexpr int QG = HILO ? MS_QG : MS_BN;   // queries per group: 128 (hi | lo columns) or 256 (hi only)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -377,9 +379,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll 1
         for (int c = half; c < nchunks; c += 2) {
           uint32_t hi[32], lo[HILO ? 32 : 1];
-          ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
-          if constexpr (HILO) ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
-          ptx::tmem_ld_wait();
+          if (exp_mode != 2 || c == half) {
+            ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
+            if constexpr (HILO) ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
+            ptx::tmem_ld_wait();
+          }
           if (c == my_last) {
             ptx::tc_fence_before();
             __syncwarp();
@@ -388,7 +392,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
             }
           }
-          if (row_ok) {
+          if (row_ok && exp_mode != 1) {
             // branch-free common case: recombine, compare against the 32 thresholds (vector loads from
             // shared memory), collect the rare hits in a bit mask; only then take the append path.
             const int qbase = g * QG + c * 32;
@@ -428,10 +432,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // compaction of this group's buffers that could overflow during the next tile
         __threadfence_block();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int qq = ew; qq < gq; qq += 8) {
-          const int q = g * QG + qq;
-          const int cnt = s_cnt[q];
-          if (cnt > MS_CAP - MS_BM) {
+        // each warp owns 32 queries of the group; one lane-parallel look at their counters (the common case
+        // — nothing close to overflowing — costs one shared load and a ballot instead of 32 dependent loads)
+        for (int qb = ew * 32; qb < gq; qb += 256) {
+          const int ql = qb + lane;
+          const int my_cnt = ql < gq ? s_cnt[g * QG + ql] : 0;
+          unsigned need = __ballot_sync(FULL, my_cnt > MS_CAP - MS_BM);
+          while (need) {
+            const int b = __ffs(need) - 1;
+            need &= need - 1;
+            const int q = g * QG + qb + b;
+            const int cnt = __shfl_sync(FULL, my_cnt, b);
             const float thr = compact_buffer(my_cand + (int64_t)q * MS_CAP, min(cnt, MS_CAP), k, lane);
             if (lane == 0) {
               s_cnt[q] = min(cnt, k);
@@ -510,8 +521,9 @@ static int scan_mma_passes(b200_index* idx, const __half* rows, int64_t n, const
     for (int pi = 0; pi < 3; pi++) {
       const int stride = strides[pi];
       if (stride > 1 && row_tiles / stride < (int64_t)(grid / 2) * 2) continue;  // too few tiles to be worth a pass
+      static const int exp_mode = getenv("B200_SCAN_EXP") ? atoi(getenv("B200_SCAN_EXP")) : 0;
       scan_mma_kernel<HILO><<<grid, MS_THREADS, smem, st>>>(tmX, tmQ, n, d, nqb, groups, k, cand, dense, stride,
-                                                            have_thr ? thr : nullptr);
+                                                            have_thr ? thr : nullptr, exp_mode);
       B200_LAUNCH_OK();
       idx->last_scan_launches++;
       if (stride == 1) B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
