@@ -116,7 +116,8 @@ int b200_index_ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
  * NULL.  Copies in, searches, copies out, synchronises. */
 int b200_index_search(b200_index* idx, const float* h_q, int nq, int k,
                       float* h_D, int64_t* h_I, float* h_R);
-/* Same with DEVICE buffers, asynchronous on `stream`. */
+/* Same with DEVICE buffers, asynchronous on `stream` — except that a batched search of more than 128
+ * queries (hi-only tensor scan) synchronises `stream` once to read how many exactness proofs failed. */
 int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k,
                              float* d_D, int64_t* d_I, float* d_R, void* stream);
 /* index.range_search(x, thresh) for ONE query (flat index; reference call sites clip_filter.py:52 and
