@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-Wall",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("B200_NVCC_EXTRA", "").split()   # e.g. -DB200_TIMING_EXPERIMENTS for tools/gemm_exp.sh, tools/scan_exp.sh
 
 
 def _nvcc():

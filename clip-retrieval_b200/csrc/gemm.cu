@@ -120,15 +120,24 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   const int bn = gemm_pick_bn(M, N, sms);
   CUtensorMap tmA, tmB;
   B200_TRY(make_tmap_2d(&tmA, d_A, 1, (uint64_t)M, (uint64_t)K, (uint64_t)K, GEMM_BM, GEMM_BK));
+  // Timing experiments (library built with -DB200_TIMING_EXPERIMENTS only; ignored otherwise).
   // B200_GEMM_HALFB=1 (timing experiment, wrong numbers): each CTA of a pair loads only 64 of its 128 B rows,
   // i.e. the operand traffic a 2-pair cluster with a multicast B tile would have (48 instead of 64 B/clk/SM).
+#ifdef B200_TIMING_EXPERIMENTS
   static const bool half_b = getenv("B200_GEMM_HALFB") != nullptr;
+#else
+  static const bool half_b = false;
+#endif
   const bool exp_half = half_b && bn == GEMM_MODE_PAIR;
   B200_TRY(make_tmap_2d(&tmB, d_W, 1, (uint64_t)N, (uint64_t)K, (uint64_t)K,
                         bn == GEMM_MODE_PAIR ? (exp_half ? 64u : 128u) : (uint32_t)bn, GEMM_BK));
   GemmEpilogue ep;
   if (exp_half) ep.exp_b_bytes = 64 * GEMM_BK * 2;
+#ifdef B200_TIMING_EXPERIMENTS
   static const bool no_ldtm = getenv("B200_GEMM_NOLDTM") != nullptr;   // timing experiment: epilogue without tcgen05.ld
+#else
+  static const bool no_ldtm = false;
+#endif
   if (no_ldtm && bn == GEMM_MODE_PAIR) ep.exp_skip_tmem = 1;
   ep.bias = d_bias;
   ep.residual = (const __nv_bfloat16*)d_residual;

@@ -90,8 +90,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
                                 n_blk * G2_BN + (int)rank * 128);
           // The peer's loads complete on the leader's barrier too (peer bit cleared in the TMA); the peer
           // cannot run a ring cycle ahead because its empty[] is released by the leader's MMA commit.
+#ifdef B200_TIMING_EXPERIMENTS
           if (leader)
             ptx::mbar_arrive_expect_tx(&full[stage], 2 * (G2_A_BYTES + (ep.exp_b_bytes ? ep.exp_b_bytes : G2_B_BYTES)));
+#else
+          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+#endif
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -177,12 +181,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       for (int ci = 0; ci < CPW; ci++) {
         const int c = half * CPW + ci;
         uint32_t r[32];
-        if (!ep.exp_skip_tmem) {
-          ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
-          ptx::tmem_ld_wait();
-        } else {
+#ifdef B200_TIMING_EXPERIMENTS
+        if (ep.exp_skip_tmem) {
 #pragma unroll
           for (int j = 0; j < 32; j++) r[j] = 0x3f800000u;
+        } else
+#endif
+        {
+          ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          ptx::tmem_ld_wait();
         }
         if (ci == CPW - 1) {
           ptx::tc_fence_before();

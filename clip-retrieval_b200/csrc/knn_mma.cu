@@ -379,7 +379,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll 1
         for (int c = half; c < nchunks; c += 2) {
           uint32_t hi[32], lo[HILO ? 32 : 1];
-          if (exp_mode != 2 || c == half) {
+#ifdef B200_TIMING_EXPERIMENTS
+          if (exp_mode != 2 || c == half)
+#endif
+          {
             ptx::tmem_ld_32x32b_x32(tbase + c * 32, hi);
             if constexpr (HILO) ptx::tmem_ld_32x32b_x32(tbase + MS_QG + c * 32, lo);
             ptx::tmem_ld_wait();
@@ -392,7 +395,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
             }
           }
+#ifdef B200_TIMING_EXPERIMENTS
           if (row_ok && exp_mode != 1) {
+#else
+          if (row_ok) {
+#endif
             // branch-free common case: recombine, compare against the 32 thresholds (vector loads from
             // shared memory), collect the rare hits in a bit mask; only then take the append path.
             const int qbase = g * QG + c * 32;
@@ -521,7 +528,11 @@ static int scan_mma_passes(b200_index* idx, const __half* rows, int64_t n, const
     for (int pi = 0; pi < 3; pi++) {
       const int stride = strides[pi];
       if (stride > 1 && row_tiles / stride < (int64_t)(grid / 2) * 2) continue;  // too few tiles to be worth a pass
+#ifdef B200_TIMING_EXPERIMENTS
       static const int exp_mode = getenv("B200_SCAN_EXP") ? atoi(getenv("B200_SCAN_EXP")) : 0;
+#else
+      const int exp_mode = 0;
+#endif
       scan_mma_kernel<HILO><<<grid, MS_THREADS, smem, st>>>(tmX, tmQ, n, d, nqb, groups, k, cand, dense, stride,
                                                             have_thr ? thr : nullptr, exp_mode);
       B200_LAUNCH_OK();

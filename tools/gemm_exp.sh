@@ -1,3 +1,4 @@
+# needs the library built with: B200_NVCC_EXTRA=-DB200_TIMING_EXPERIMENTS python clip-retrieval_b200/build.py -f
 # A/B of the pair GEMM under sustained clocks: baseline, epilogue without the TMEM read-out, half of B loaded.
 for v in "" "B200_GEMM_NOLDTM=1" "B200_GEMM_HALFB=1" "B200_GEMM_NOLDTM=1 B200_GEMM_HALFB=1" ""; do
   echo "== ${v:-baseline}"
