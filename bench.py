@@ -287,9 +287,9 @@ def run_b200(args):
                         "roofline": kn["roofline"], "e2e": kn["e2e"], "gpu_launches": kn["gpu_launches"], "knn": kn})
 
     if rank == 0 and world >= 1:
-        if args.workload == "vitl14" and not args.no_cpu:
+        if args.workload == "vitl14" and not args.no_cpu and world == 1:   # rank 0 at N=1 only
             out["cpu_baseline"] = cpu_baseline_embed(arch_name, args.cpu_sample)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -383,7 +383,7 @@ def run_reference(args):
         best = cb if best is None or cb["value"] > best["value"] else best
         if time.perf_counter() - t_all > 150:
             break
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "ViT-L/14 embeds/s (image+text pairs/s)", "value": best["value"], "unit": "pairs/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 1, "ms_per_step": 1e3 * n / best["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -391,10 +391,34 @@ def run_reference(args):
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's own path (all_clip/open_clip) cannot be installed offline; this is the CPU oracle port (oracle/clip_ref.py)",
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Library chatter (e.g. the NCCL version banner) must not share stdout with the one JSON line:
+    route fd 1 to stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
