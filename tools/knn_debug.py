@@ -14,7 +14,8 @@ idx.reserve(n)
 idx.add_synthetic(n, m.SynthSpec(seed=1234))
 torch.cuda.synchronize()
 print("index ready: ntotal=%d (%.1f GB)" % (idx.ntotal, n * d * 2 / 1e9))
-for nq in (1, 4, 8, 128, 256, 512, 1000):
+nqs = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1, 4, 8, 128, 256, 512, 1000)
+for nq in nqs:
     q = synth_rows(nq, d, m.SynthSpec(seed=4321), dtype="float32")
     for k in (40,):
         for _ in range(2):
