@@ -18,9 +18,9 @@
 // that reaches the query's current threshold is appended to the (CTA, query) candidate buffer
 // (atomic counter in shared memory, buffer in global/L2); buffers are compacted to their k best by
 // the epilogue warps between tiles, which raises the threshold.  A final select merges the CTAs.
-// Thresholds are warmed up by two sampling passes (every 1024th, then every 32nd row tile: the k-th
-// best score of a subset is a valid lower bound for the full set), so the full pass almost never
-// takes the append path.
+// Thresholds are warmed up by two sampling passes (one row tile per CTA pair, then every 32nd row
+// tile: the k-th best score of a subset is a valid lower bound for the full set), so the full pass
+// almost never takes the append path.
 // Roofline: tensor pipe (4*N*d*nq flops with the split) for large nq, HBM (N*d*2 bytes per 128
 // queries) below ~64 queries per pass.  ncu (profiles/r01f_final_summary.txt): one 128-query group
 // over 20M x 768 rows takes 4.64 ms with the tensor pipe 98 % active AND 30.7 GB read from DRAM
@@ -522,12 +522,19 @@ static int scan_mma_passes(b200_index* idx, const __half* rows, int64_t n, const
     int C = 2048;
     while (C < 2 * k) C <<= 1;
     unsigned long long* keys_q = d_keys_out + (size_t)q0 * k;
-    const int strides[3] = {1024, 32, 1};
+    // Pass schedule.  The first pass starts from -inf thresholds, where EVERY score is appended and the
+    // buffers are compacted every third tile (ncu: 2.55 ms for 3 % of the tiles at 4 % tensor-active), so it
+    // is kept to one tile per CTA pair (a sample of npairs*256 rows, no compaction before the final one);
+    // its k-th best scores seed a 1/32 pass, whose k-th best scores seed the full pass.
+    const int64_t npairs = grid / 2;
+    int strides[3], npass = 0;
+    if (row_tiles >= 8 * npairs) strides[npass++] = (int)std::min<int64_t>(row_tiles / npairs, 1 << 30);
+    if (npass == 1 && strides[0] > 64 && row_tiles / 32 >= 2 * npairs) strides[npass++] = 32;
+    strides[npass++] = 1;
     bool have_thr = false;
     B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
-    for (int pi = 0; pi < 3; pi++) {
+    for (int pi = 0; pi < npass; pi++) {
       const int stride = strides[pi];
-      if (stride > 1 && row_tiles / stride < (int64_t)(grid / 2) * 2) continue;  // too few tiles to be worth a pass
 #ifdef B200_TIMING_EXPERIMENTS
       static const int exp_mode = getenv("B200_SCAN_EXP") ? atoi(getenv("B200_SCAN_EXP")) : 0;
 #else
