@@ -2,12 +2,13 @@
 //   C[M,N] = epilogue(A[M,K] · W[N,K]^T)     A, W bf16 row-major (both "K-major"), fp32 accumulate.
 //
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (W) boxes, 128B swizzle,
-//               into a 4-stage shared-memory ring guarded by full/empty mbarriers;
-//   warp 1      allocates the 512 TMEM columns and issues tcgen05.mma (128 x BN x 16 per instruction,
+//   warp 8      TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (W) boxes, 128B swizzle,
+//               into a 4..6-stage shared-memory ring guarded by full/empty mbarriers;
+//   warp 9      allocates the 512 TMEM columns and issues tcgen05.mma (128 x BN x 16 per instruction,
 //               4 per stage); tcgen05.commit releases ring slots and publishes finished accumulators;
-//   warps 2..5  epilogue: tcgen05.ld of the fp32 accumulator (each thread owns one output row),
-//               + bias, activation, + residual, bf16 pack, 16-byte global stores.
+//   warps 0..7  epilogue, two warps per TMEM lane quarter splitting the tile's columns: tcgen05.ld of
+//               the fp32 accumulator (each thread owns one output row), + bias, activation,
+//               + residual, bf16 pack, 16-byte global stores.
 // Two accumulator stages (2 x BN columns of TMEM) let the epilogue of tile i overlap the main loop
 // of tile i+1.  Tiles are walked in groups of 16 row-blocks x all column-blocks so the activation
 // rows of a group stay in L2 while the weights (a few MB) are re-read from L2, not HBM.
@@ -21,7 +22,7 @@ namespace b200 {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per SM sub-partition)
+constexpr int GEMM_THREADS = 320;  // warps 0..7 epilogue (two per SM sub-partition), warp 8 TMA, warp 9 MMA
 constexpr int GEMM_GROUP_M = 16;
 // Warp roles.  The two single-thread roles sit on the HIGHEST warp ids: the sub-partition arbiter
 // favours higher warp ids, and an MMA issuer starved by busy epilogue warps shows up as tensor-pipe
@@ -240,7 +241,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
+    // ---------------- epilogue (warps 0..7) ----------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int et = warp * 32 + lane;  // 0..255 (epilogue warps are warps 0..7)
     const int half = warp >> 2;        // which half of the tile columns this warp drains

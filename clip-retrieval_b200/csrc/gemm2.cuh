@@ -7,9 +7,9 @@
 // both halves across the pair.  Operand traffic drops to 32 KB per k-block per SM and the ring
 // deepens to 6 stages in the same shared memory.
 //
-// Roles per CTA: warp 0 TMA producer (its A half + its B half; completion bytes are credited to
-// the leader's full barrier), warp 1 = MMA issuer in the leader CTA only, warps 2..5 epilogue over
-// this CTA's 128 accumulator rows.  tcgen05.commit multicasts "slot free" / "accumulator ready" to
+// Roles per CTA (gemm.cuh): warp 8 TMA producer (its A half + its B half; completion bytes are credited
+// to the leader's full barrier), warp 9 = MMA issuer in the leader CTA only, warps 0..7 epilogue over
+// this CTA's 128 accumulator rows (two warps per TMEM lane quarter, each draining half of the columns).  tcgen05.commit multicasts "slot free" / "accumulator ready" to
 // the barriers of both CTAs; epilogue warps of both CTAs release the accumulator stage on the
 // leader's barrier (remote mbarrier arrive for the second CTA).
 #pragma once
@@ -142,9 +142,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue (warps 2..5 of both CTAs) ----------------
+    // ---------------- epilogue (warps 0..7 of both CTAs) ----------------
     const int q = warp & 3;
-    const int et = warp * 32 + lane;  // 0..255 (epilogue warps are warps 0..7)
+    const int et = warp * 32 + lane;  // 0..255
     const int half = warp >> 2;        // which half of the tile columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;

@@ -11,9 +11,10 @@
 // epilogue (22 significant bits of the query: below the fp32 accumulation noise already accepted
 // for the FMA kernel).
 //
-// Structure = the GEMM core (gemm.cuh): warp 0 TMA producer (X box 128x64, Q' box 256x64, 128B
-// swizzle, 4-stage ring), warp 1 MMA issuer (128x256x16, two TMEM accumulator stages), warps 2..5
-// epilogue.  A CTA owns whole 128-row tiles (tile = cta + i*grid) and walks all query groups of a
+// Structure = the pair GEMM core (gemm2.cuh): warp 0 TMA producer (X box 128x64, half of the Q' box
+// per CTA, 128B swizzle, 6-stage ring), warp 1 MMA issuer (cta_group::2, 256x256x16, two TMEM
+// accumulator stages), warps 2..9 epilogue (two per TMEM lane quarter, alternate 32-column chunks).
+// A CTA pair owns whole 256-row tiles (tile = pair + i*npairs) and walks all query groups of a
 // tile back to back, so the X tile is re-read from L2, not HBM.  Epilogue: thread = row; a score
 // that reaches the query's current threshold is appended to the (CTA, query) candidate buffer
 // (atomic counter in shared memory, buffer in global/L2); buffers are compacted to their k best by
