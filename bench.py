@@ -29,6 +29,10 @@ sys.path.insert(0, ROOT)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+# The reference's published ViT-L/14 numbers: samples/s by GPU count, A100.
+PUBLISHED_VITL14 = {1: 312.0, 8: 2500.0}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -251,7 +255,10 @@ def run_b200(args):
         out.update({
             "metric": "ViT-L/14 embeds/s (image+text pairs/s)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 (fp32 accumulate, fp32 LN/softmax/norm; fp16 output)", "data": "synthetic",
+            "vs_baseline": (value / PUBLISHED_VITL14[world]) if world in PUBLISHED_VITL14 else None,
+            "baseline_note": "BASELINE.md: reference ViT-L/14 embed throughput 312 sample/s on 1 A100, 2500 on 8 "
+                             "(docs/distributed_clip_inference.md:205; its own reader/writer included)",
+            "dtype": "bf16 (fp32 accumulate, fp32 LN/softmax/norm; fp16 output)", "data": "synthetic",
             "config": {"workload": "ViT-L/14 image+text inference, synthetic 224^2, batch %d per GPU (BASELINE configs[1])" % B,
                        "global_batch": B * world, "parallelism": "dp%d (independent replicas, no collective)" % world,
                        "weights": "seeded random init", "l2": "inputs (616.6 MB/step) larger than L2"},
