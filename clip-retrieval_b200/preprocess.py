@@ -32,6 +32,22 @@ def to_rgb8(image):
     return np.ascontiguousarray(a)
 
 
+def pack_images(images):
+    """-> (uint8 buffer, int64 offsets, int32 heights, int32 widths): the C-ABI batch layout of
+    b200_preproc_run (images back to back, RGB uint8 HWC)."""
+    arrs = [to_rgb8(im) for im in images]
+    heights = np.array([a.shape[0] for a in arrs], np.int32)
+    widths = np.array([a.shape[1] for a in arrs], np.int32)
+    sizes = heights.astype(np.int64) * widths * 3
+    offsets = np.zeros(len(arrs), np.int64)
+    if len(arrs) > 1:
+        offsets[1:] = np.cumsum(sizes[:-1])
+    buf = np.empty(int(sizes.sum()), np.uint8)
+    for a, o, s in zip(arrs, offsets, sizes):
+        buf[o:o + s] = a.reshape(-1)
+    return buf, offsets, heights, widths
+
+
 class B200Preprocess:
     def __init__(self, n_px=224, mean=OPENAI_MEAN, std=OPENAI_STD, device=None):
         if device is None:
@@ -50,18 +66,7 @@ class B200Preprocess:
             lib.b200_preproc_destroy(h)
 
     def pack(self, images):
-        """-> (uint8 buffer, int64 offsets, int32 heights, int32 widths): the C-ABI batch layout."""
-        arrs = [to_rgb8(im) for im in images]
-        heights = np.array([a.shape[0] for a in arrs], np.int32)
-        widths = np.array([a.shape[1] for a in arrs], np.int32)
-        sizes = heights.astype(np.int64) * widths * 3
-        offsets = np.zeros(len(arrs), np.int64)
-        if len(arrs) > 1:
-            offsets[1:] = np.cumsum(sizes[:-1])
-        buf = np.empty(int(sizes.sum()), np.uint8)
-        for a, o, s in zip(arrs, offsets, sizes):
-            buf[o:o + s] = a.reshape(-1)
-        return buf, offsets, heights, widths
+        return pack_images(images)
 
     def run_packed(self, pixels, offsets, heights, widths, out=None):
         """pixels: uint8 numpy buffer (host) or uint8 cuda tensor; returns float32 [n,3,n_px,n_px]."""

@@ -66,3 +66,25 @@ def test_oracle_matches_reference_fixtures():
             assert np.array_equal(P.preprocess(px), t.numpy()), name
             seen += 1
     assert seen == 7
+
+
+def test_pack_images_layout_and_mode_conversion():
+    """Host side of the GPU transform: the packed batch layout of b200_preproc_run and the RGB conversion
+    (no CUDA involved)."""
+    from PIL import Image
+    from clip_retrieval_b200.preprocess import pack_images, to_rgb8
+
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    g = rng.integers(0, 256, (4, 3), dtype=np.uint8)
+    buf, off, hh, ww = pack_images([a, Image.fromarray(g, mode="L"), Image.fromarray(a).convert("RGBA")])
+    assert hh.tolist() == [5, 4, 5] and ww.tolist() == [7, 3, 7]
+    assert off.tolist() == [0, 105, 141] and buf.size == 105 + 36 + 105 and buf.dtype == np.uint8
+    assert np.array_equal(buf[:105].reshape(5, 7, 3), a)
+    assert np.array_equal(buf[105:141].reshape(4, 3, 3), np.repeat(g[:, :, None], 3, axis=2))
+    assert np.array_equal(buf[141:].reshape(5, 7, 3), a)
+    assert np.array_equal(to_rgb8(g), np.repeat(g[:, :, None], 3, axis=2))
+    with pytest.raises(ValueError):
+        to_rgb8(np.zeros((4, 4, 3), np.float32))
+    e = pack_images([])
+    assert e[0].size == 0 and e[1].size == 0
