@@ -113,3 +113,81 @@ def test_postfilter_oracle_known_answers():
     assert R.get_non_uniques(E, 0.94) == [2, 3]
     P = np.stack([e[1], e[0], e[2]])
     np.testing.assert_array_equal(R.get_violent_items(P, E), [0, 2, 3])
+
+
+REF_BACK = "/root/reference/clip_retrieval/clip_back.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BACK), reason="reference checkout not present (GPU box)")
+def test_postfilter_oracle_matches_reference_functions():
+    """Pins oracle/postfilter_ref.py on the reference's OWN code: `KnnService.connected_components` and
+    `get_violent_items` (clip_back.py:270-288,321-324) are dependency-free methods, so their source is
+    extracted from the reference file with `ast` and executed here (clip_back itself cannot be imported:
+    flask / faiss are absent) and compared with the restatement on random graphs."""
+    import ast
+    import textwrap
+    from collections import defaultdict
+    from oracle import postfilter_ref as R
+
+    src = open(REF_BACK).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "KnnService")
+    fns = {}
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("connected_components", "get_violent_items"):
+            ns = {"np": np}
+            exec(textwrap.dedent(ast.get_source_segment(src, node)), ns)   # the reference's code, unmodified
+            fns[node.name] = ns[node.name]
+    assert set(fns) == {"connected_components", "get_violent_items"}
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        k = int(rng.integers(2, 60))
+        A = rng.random((k, k)) < 0.05
+        A = A | A.T | np.eye(k, dtype=bool)
+        neigh = defaultdict(list)
+        for i in range(k):
+            for j in np.nonzero(A[i])[0]:
+                neigh[int(i)].append(int(j))
+        ref_groups = fns["connected_components"](None, neigh)
+        ref_drop = sorted(e for g in ref_groups for e in g[1:])
+        assert R.get_non_uniques(None, adjacency=A) == ref_drop
+        assert sorted(map(sorted, R.connected_components(neigh))) == sorted(map(sorted, ref_groups))
+    E = rng.standard_normal((200, 64)).astype(np.float32)
+    P = rng.standard_normal((3, 64)).astype(np.float32)
+    np.testing.assert_array_equal(R.get_violent_items(P, E), fns["get_violent_items"](None, P, E))
+
+
+REF_MAPPER = "/root/reference/clip_retrieval/clip_inference/mapper.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MAPPER), reason="reference checkout not present (GPU box)")
+def test_mapper_glue_matches_reference_call():
+    """The reference's own `ClipMapper.__call__` (mapper.py:49-78) — extracted with `ast`, executed unmodified
+    with the oracle's encoders standing in for `model.encode_image/encode_text` (all_clip is not installable)
+    — must return exactly what oracle.clip_ref.mapper_image / mapper_text return: this pins the normalise +
+    fp16-cast glue and the five-key output contract on the reference's code, bit for bit."""
+    import ast
+    import textwrap
+    import types
+    import torch
+
+    src = open(REF_MAPPER).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ClipMapper")
+    call = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__call__")
+    ns = {"torch": torch, "np": np}
+    exec(textwrap.dedent(ast.get_source_segment(src, call)), ns)
+    cfg = clip_ref.CONFIGS["tiny"]
+    sd = clip_ref.make_state_dict(cfg, seed=0)
+    px = clip_ref.synth_images(5, cfg, seed=1)
+    tk = clip_ref.synth_tokens(5, cfg, seed=1)
+    me = types.SimpleNamespace(enable_image=True, enable_text=True, enable_metadata=True, use_mclip=False, device="cpu",
+                               model_img=lambda x: clip_ref.encode_image(sd, cfg, x),
+                               model_txt=lambda x: clip_ref.encode_text(sd, cfg, x))
+    item = {"image_tensor": px, "text_tokens": tk, "image_filename": list("abcde"), "text": list("vwxyz"), "metadata": list("12345")}
+    out = ns["__call__"](me, item)
+    assert list(out) == ["image_embs", "text_embs", "image_filename", "text", "metadata"]
+    assert out["image_embs"].dtype == np.float16 and out["text_embs"].dtype == np.float16
+    assert np.array_equal(out["image_embs"], clip_ref.mapper_image(sd, cfg, px))
+    assert np.array_equal(out["text_embs"], clip_ref.mapper_text(sd, cfg, tk))
+    assert out["image_filename"] == list("abcde") and out["text"] == list("vwxyz") and out["metadata"] == list("12345")
