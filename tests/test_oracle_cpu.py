@@ -191,3 +191,44 @@ def test_mapper_glue_matches_reference_call():
     assert np.array_equal(out["image_embs"], clip_ref.mapper_image(sd, cfg, px))
     assert np.array_equal(out["text_embs"], clip_ref.mapper_text(sd, cfg, tk))
     assert out["image_filename"] == list("abcde") and out["text"] == list("vwxyz") and out["metadata"] == list("12345")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BACK), reason="reference checkout not present (GPU box)")
+def test_index_contract_through_reference_knn_search():
+    """The reference's own `KnnService.knn_search` + `post_filter` + `normalized` (clip_back.py:194-197,313-399),
+    extracted with `ast` and executed unmodified, driven by an index object with the oracle's
+    `search_and_reconstruct` (the contract B200FlatIndex is tested against on the GPU): -1 padding when
+    k > ntotal is truncated, distances stay descending, and dedup runs on the reconstructed rows."""
+    import ast
+    import contextlib
+    import textwrap
+    import types
+    from oracle import postfilter_ref as R
+
+    src = open(REF_BACK).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "KnnService")
+    timer = types.SimpleNamespace(time=lambda: contextlib.nullcontext())
+    ns = {"np": np, "KNN_INDEX_TIME": timer, "DEDUP_TIME": timer, "SAFETY_TIME": timer}
+    norm = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "normalized")
+    exec(ast.get_source_segment(src, norm), ns)
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("knn_search", "post_filter", "connected_components_dedup"):
+            exec(textwrap.dedent(ast.get_source_segment(src, node)), ns)
+
+    d, n = 64, 30
+    X = synth_ref.rows_f16(n, d)
+    X[7] = X[3]                                     # an exact duplicate pair: dedup must drop the later hit
+    index = types.SimpleNamespace(search_and_reconstruct=lambda q, k: knn_ref.flat_search_and_reconstruct(X, q, k))
+    svc = types.SimpleNamespace(get_non_uniques=lambda emb, threshold=0.94: R.get_non_uniques(emb, threshold))
+    svc.connected_components_dedup = lambda emb: ns["connected_components_dedup"](svc, emb)
+    svc.post_filter = lambda *a: ns["post_filter"](svc, *a)
+    res = types.SimpleNamespace(image_index=index, text_index=index, metadata_is_ordered_by_ivf=False, safety_model=None,
+                                violence_detector=None)
+    q = X[3:4].astype(np.float32)
+    dist, ind = ns["knn_search"](svc, q, "image", 40, res, False, False, False)     # k=40 > ntotal=30 -> -1 tail
+    D, I = knn_ref.flat_search(X, q, 40)
+    assert (I[0, 30:] == -1).all() and len(ind) == 30 and [int(i) for i in ind] == I[0, :30].tolist()
+    assert np.all(np.diff(np.array(dist)) <= 0) and set(int(i) for i in ind[:2]) == {3, 7}
+    dist2, ind2 = ns["knn_search"](svc, q, "image", 40, res, True, False, False)    # with dedup
+    assert len(ind2) == 29 and int(ind2[0]) == 3 and 7 not in [int(i) for i in ind2]
