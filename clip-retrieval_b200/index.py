@@ -274,6 +274,18 @@ class B200IVFFlatIndex(_IndexBase):
         return sizes, ids
 
 
+def list_embedding_shards(path):
+    """The `.npy` shards under `path` in global row order: the reference writer names them
+    `img_emb_{id:0{w}d}.npy` with a fixed width per run (writer.py:22,67-87), so sorted file order is
+    partition order, which is the row id order autofaiss assigns."""
+    files = [path] if os.path.isfile(path) else sorted(
+        os.path.join(path, f) for f in os.listdir(path) if f.endswith(".npy")
+    )
+    if not files:
+        raise ValueError("load_index: no .npy shard under %s" % path)
+    return files
+
+
 def load_index(path, enable_faiss_memory_mapping=False, device=0):
     """Counterpart of clip_back.load_index (clip_back.py:589-596) for fp16 embedding shards.
 
@@ -283,11 +295,7 @@ def load_index(path, enable_faiss_memory_mapping=False, device=0):
     straight to HBM; `enable_faiss_memory_mapping` is accepted for signature parity and ignored.
     """
     del enable_faiss_memory_mapping
-    files = [path] if os.path.isfile(path) else sorted(
-        os.path.join(path, f) for f in os.listdir(path) if f.endswith(".npy")
-    )
-    if not files:
-        raise ValueError("load_index: no .npy shard under %s" % path)
+    files = list_embedding_shards(path)
     first = np.load(files[0], mmap_mode="r")
     index = B200FlatIndex(first.shape[1], device=device)
     total = sum(np.load(f, mmap_mode="r").shape[0] for f in files)
