@@ -74,7 +74,10 @@ struct b200_clip {
   cudaStream_t s_copy = nullptr, s_comp = nullptr;   // host entry: H2D of sub-batch i+1 overlaps compute of i
   cudaEvent_t ev_in[4] = {}, ev_done[4] = {};
   std::vector<void*> allocs;
-  std::mutex mu;
+  std::mutex mu;                  // held by every encode entry (host and device) while it enqueues
+  cudaEvent_t act_ev = nullptr;   // end of the last forward; a forward on another stream waits on it
+  cudaStream_t act_stream = nullptr;
+  bool act_used = false;
   // timing
   bool profiling = false;
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
@@ -373,6 +376,7 @@ int b200_clip_destroy(b200_clip* m) {
   cudaDeviceSynchronize();
   for (void* p : m->allocs) cudaFree(p);
   for (auto& s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  if (m->act_ev) cudaEventDestroy(m->act_ev);
   if (m->s_copy) {
     cudaStreamDestroy(m->s_copy); cudaStreamDestroy(m->s_comp);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_done[i]); }
@@ -441,13 +445,37 @@ static int encode_device(b200_clip* m, const void* d_in, int B, void* d_out, int
   return B200_OK;
 }
 
+// The activation buffers of a handle are shared by every forward on it: calls hold m->mu while they enqueue,
+// and a call on a different stream than the previous one first waits (event) for the previous forward's kernels.
+static int act_acquire(b200_clip* m, cudaStream_t st) {
+  if (!m->act_ev) B200_CUDA(cudaEventCreateWithFlags(&m->act_ev, cudaEventDisableTiming));
+  if (m->act_used && m->act_stream != st) B200_CUDA(cudaStreamWaitEvent(st, m->act_ev, 0));
+  return B200_OK;
+}
+static int act_release(b200_clip* m, cudaStream_t st) {
+  B200_CUDA(cudaEventRecord(m->act_ev, st));
+  m->act_stream = st;
+  m->act_used = true;
+  return B200_OK;
+}
+static int encode_device_locked(b200_clip* m, const void* d_in, int B, void* d_out, int out_dtype, int normalize,
+                                bool image, cudaStream_t st) {
+  B200_CHECK(m, B200_ERR_INVALID, "encode: null handle");
+  std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard g(m->device);
+  B200_TRY(act_acquire(m, st));
+  const int rc = encode_device(m, d_in, B, d_out, out_dtype, normalize, image, st);
+  B200_TRY(act_release(m, st));
+  return rc;
+}
+
 int b200_clip_encode_image_device(b200_clip* m, const float* d_pixels, int B, void* d_out, int out_dtype, int normalize,
                                   void* stream) {
-  return encode_device(m, d_pixels, B, d_out, out_dtype, normalize, true, (cudaStream_t)stream);
+  return encode_device_locked(m, d_pixels, B, d_out, out_dtype, normalize, true, (cudaStream_t)stream);
 }
 int b200_clip_encode_text_device(b200_clip* m, const int64_t* d_tokens, int B, void* d_out, int out_dtype, int normalize,
                                  void* stream) {
-  return encode_device(m, d_tokens, B, d_out, out_dtype, normalize, false, (cudaStream_t)stream);
+  return encode_device_locked(m, d_tokens, B, d_out, out_dtype, normalize, false, (cudaStream_t)stream);
 }
 
 // Host-buffer entry (the mapper call).  Images are pipelined in sub-batches: the H2D copy of
@@ -466,6 +494,7 @@ static int encode_host(b200_clip* m, const void* h_in, int B, void* h_out, int o
       B200_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
     }
   }
+  B200_TRY(act_acquire(m, m->s_comp));
   const int mb = m->cfg.max_batch;
   const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
   const size_t out_stride = (size_t)m->cfg.embed_dim * (out_dtype == B200_OUT_F16 ? 2 : 4);
@@ -494,6 +523,7 @@ static int encode_host(b200_clip* m, const void* h_in, int B, void* h_out, int o
                               m->s_comp));
   }
   B200_CUDA(cudaStreamSynchronize(m->s_comp));
+  B200_TRY(act_release(m, m->s_comp));
   m->last_launches = launches;
   return B200_OK;
 }

@@ -37,7 +37,10 @@ struct b200_index {
   // scratch
   void* ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0: scan internals; 1..3: callers; 4,5: hi-only mode
   size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
-  std::mutex mu;
+  std::mutex mu;             // every search entry (host and device) holds it while it enqueues work
+  cudaEvent_t scratch_ev = nullptr;   // recorded after the last search's launches: the next search on ANOTHER
+  cudaStream_t scratch_stream = nullptr;   // stream waits on it before it reuses ws[] / norm_bound[]
+  bool scratch_used = false;
 
   // scan timing (CUDA events on the launching stream)
   std::vector<cudaEvent_t> ev;   // pairs

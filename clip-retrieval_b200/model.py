@@ -41,18 +41,49 @@ class ClipArch:
     quick_gelu: bool = True
 
 
-# Architectures the reference's docs and tests name (README.md:179,201; docs/laion5B_h14_back.md:60).
+# Architectures the reference's docs and tests name (README.md:179,201,237; docs/laion5B_h14_back.md:60;
+# tests/test_clip_inference/test_mapper.py:11-15).  Keys are the *architecture*; the activation follows the
+# checkpoint family (OpenAI weights: QuickGELU; LAION open_clip weights: erf GELU) and is resolved by
+# `resolve_arch` from the name's suffix / pretrained tag, as open_clip's factory does.
+_B32 = (512, 224, 32, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048))
+_B16 = (512, 224, 16, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048))
+_L14 = (768, 224, 14, Tower(1024, 24, 16, 4096), Tower(768, 12, 12, 3072))
+_L14_336 = (768, 336, 14, Tower(1024, 24, 16, 4096), Tower(768, 12, 12, 3072))
+_H14 = (1024, 224, 14, Tower(1280, 32, 16, 5120), Tower(1024, 24, 16, 4096))
+_B32_256 = (512, 256, 32, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048))
+
 ARCHS = {
-    "ViT-B/32": ClipArch(512, 224, 32, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048), quick_gelu=True),
-    "ViT-B/16": ClipArch(512, 224, 16, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048), quick_gelu=True),
-    "ViT-L/14": ClipArch(768, 224, 14, Tower(1024, 24, 16, 4096), Tower(768, 12, 12, 3072), quick_gelu=True),
-    "ViT-L/14@336px": ClipArch(768, 336, 14, Tower(1024, 24, 16, 4096), Tower(768, 12, 12, 3072), quick_gelu=True),
-    "open_clip:ViT-B-32": ClipArch(512, 224, 32, Tower(768, 12, 12, 3072), Tower(512, 12, 8, 2048), quick_gelu=False),
-    "open_clip:ViT-L-14": ClipArch(768, 224, 14, Tower(1024, 24, 16, 4096), Tower(768, 12, 12, 3072), quick_gelu=False),
-    "open_clip:ViT-H-14": ClipArch(1024, 224, 14, Tower(1280, 32, 16, 5120), Tower(1024, 24, 16, 4096), quick_gelu=False),
-    "open_clip:ViT-g-14": ClipArch(1024, 224, 14, Tower(1408, 40, 16, 6144), Tower(1024, 24, 16, 4096), quick_gelu=False),
+    # bare names -> OpenAI clip.load (QuickGELU)
+    "ViT-B/32": ClipArch(*_B32, quick_gelu=True),
+    "ViT-B/16": ClipArch(*_B16, quick_gelu=True),
+    "ViT-L/14": ClipArch(*_L14, quick_gelu=True),
+    "ViT-L/14@336px": ClipArch(*_L14_336, quick_gelu=True),
+    # open_clip model configs (erf GELU unless `-quickgelu` / pretrained tag `openai`)
+    "open_clip:ViT-B-32": ClipArch(*_B32, quick_gelu=False),
+    "open_clip:ViT-B-32-256": ClipArch(*_B32_256, quick_gelu=False),
+    "open_clip:ViT-B-16": ClipArch(*_B16, quick_gelu=False),
+    "open_clip:ViT-L-14": ClipArch(*_L14, quick_gelu=False),
+    "open_clip:ViT-L-14-336": ClipArch(*_L14_336, quick_gelu=False),
+    "open_clip:ViT-H-14": ClipArch(*_H14, quick_gelu=False),
 }
 ARCHS["ViT-H/14"] = ARCHS["open_clip:ViT-H-14"]
+
+# `hf_clip:<repo>` names -> (architecture key, quick_gelu): HuggingFace CLIPModel checkpoints of the same towers.
+HF_REPOS = {
+    "openai/clip-vit-base-patch32": ("open_clip:ViT-B-32", True),
+    "openai/clip-vit-base-patch16": ("open_clip:ViT-B-16", True),
+    "openai/clip-vit-large-patch14": ("open_clip:ViT-L-14", True),
+    "openai/clip-vit-large-patch14-336": ("open_clip:ViT-L-14-336", True),
+    "patrickjohncyh/fashion-clip": ("open_clip:ViT-B-32", True),      # fine-tuned from openai/clip-vit-base-patch32
+    "laion/CLIP-ViT-B-32-laion2B-s34B-b79K": ("open_clip:ViT-B-32", False),
+    "laion/CLIP-ViT-L-14-laion2B-s32B-b82K": ("open_clip:ViT-L-14", False),
+    "laion/CLIP-ViT-H-14-laion2B-s32B-b79K": ("open_clip:ViT-H-14", False),
+}
+# `nm:<repo>` (DeepSparse, README.md:201) names quantised ONNX exports of these open_clip towers.
+NM_REPOS = {
+    "neuralmagic/CLIP-ViT-B-32-256x256-DataComp-s34B-b86K-quant-ds": ("open_clip:ViT-B-32-256", False),
+    "mgoin/CLIP-ViT-B-32-laion2b_s34b_b79k-ds": ("open_clip:ViT-B-32", False),
+}
 
 
 def _torch():
@@ -61,13 +92,49 @@ def _torch():
     return torch
 
 
+def arch_from_hf_config(cfg):
+    """ClipArch from a HuggingFace CLIPConfig dict (config.json of an `hf_clip:` repo)."""
+    v, t = cfg["vision_config"], cfg["text_config"]
+    act = v.get("hidden_act", "quick_gelu")
+    if act not in ("quick_gelu", "gelu"):
+        raise ValueError("hf_clip: activation %r not supported" % act)
+    return ClipArch(int(cfg.get("projection_dim", v.get("projection_dim", 512))), int(v.get("image_size", 224)),
+                    int(v.get("patch_size", 32)),
+                    Tower(int(v["hidden_size"]), int(v["num_hidden_layers"]), int(v["num_attention_heads"]), int(v["intermediate_size"])),
+                    Tower(int(t["hidden_size"]), int(t["num_hidden_layers"]), int(t["num_attention_heads"]), int(t["intermediate_size"])),
+                    int(t.get("max_position_embeddings", 77)), int(t.get("vocab_size", 49408)), quick_gelu=(act == "quick_gelu"))
+
+
 def resolve_arch(clip_model):
-    """Map a reference `clip_model` string to (arch, key).  `open_clip:ARCH/PRETRAINED` keeps ARCH."""
+    """Map a reference `clip_model` string to (arch, key) the way all_clip's dispatcher reads it
+    (README.md:179,201,237): bare names are OpenAI checkpoints (QuickGELU); `open_clip:ARCH[/PRETRAINED]`
+    is an open_clip model config, QuickGELU when ARCH ends in `-quickgelu` or PRETRAINED is `openai`
+    (open_clip's factory forces it for OpenAI weights); `hf_clip:REPO` / `nm:REPO` name a known repo."""
+    from dataclasses import replace
+
     name = clip_model
     if name.startswith("synthetic:"):
         name = name[len("synthetic:"):]
     if name.startswith("open_clip:"):
-        name = "open_clip:" + name[len("open_clip:"):].split("/")[0]
+        spec = name[len("open_clip:"):]
+        arch_name, _, pretrained = spec.partition("/")
+        quick = False
+        if arch_name.endswith("-quickgelu"):
+            arch_name, quick = arch_name[: -len("-quickgelu")], True
+        if pretrained == "openai":
+            quick = True
+        key = "open_clip:" + arch_name
+        if key not in ARCHS:
+            raise ValueError("unknown clip_model %r; known: %s" % (clip_model, ", ".join(sorted(ARCHS))))
+        return replace(ARCHS[key], quick_gelu=quick), key + ("-quickgelu" if quick else "")
+    for prefix, table in (("hf_clip:", HF_REPOS), ("nm:", NM_REPOS)):
+        if name.startswith(prefix):
+            repo = name[len(prefix):]
+            if repo not in table:
+                raise ValueError("unknown %s repository %r; known: %s (or load a state_dict with "
+                                 "B200Clip(arch_from_hf_config(config)))" % (prefix, repo, ", ".join(sorted(table))))
+            key, quick = table[repo]
+            return replace(ARCHS[key], quick_gelu=quick), name
     if name not in ARCHS:
         raise ValueError("unknown clip_model %r; known: %s" % (clip_model, ", ".join(sorted(ARCHS))))
     return ARCHS[name], name
@@ -318,7 +385,7 @@ class SimpleTokenizer:
     def __init__(self, bpe_path, context_length=77):
         self.context_length = context_length
         merges = gzip.open(bpe_path).read().decode("utf-8").split("\n")
-        merges = [tuple(m.split()) for m in merges[1:49152 - 256 - 2 + 1]]
+        merges = [tuple(m.split()) for m in merges[1:49152 - 256 - 2 + 1] if len(m.split()) == 2]
         self.byte_encoder = _bytes_to_unicode()
         vocab = list(self.byte_encoder.values())
         vocab = vocab + [v + "</w>" for v in vocab]
@@ -327,10 +394,11 @@ class SimpleTokenizer:
         self.encoder = {v: i for i, v in enumerate(vocab)}
         self.bpe_ranks = {m: i for i, m in enumerate(merges)}
         self.cache = {"<|startoftext|>": "<|startoftext|>", "<|endoftext|>": "<|endoftext|>"}
-        import re
+        import regex  # \p{L} / \p{N} classes: the pattern of OpenAI clip / open_clip's SimpleTokenizer
 
-        self.pat = re.compile(r"<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[a-zA-Z]+|[0-9]|[^\sa-zA-Z0-9]+",
-                              re.IGNORECASE)
+        self.pat = regex.compile(
+            r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""",
+            regex.IGNORECASE)
 
     def _bpe(self, token):
         if token in self.cache:
@@ -356,7 +424,7 @@ class SimpleTokenizer:
         return out
 
     def encode(self, text):
-        text = " ".join(html.unescape(html.unescape(text)).split()).strip().lower()
+        text = _whitespace_clean(_basic_clean(text)).lower()
         ids = []
         for tok in self.pat.findall(text):
             tok = "".join(self.byte_encoder[b] for b in tok.encode("utf-8"))
@@ -376,6 +444,27 @@ class SimpleTokenizer:
                 ids[-1] = eot
             out[i, : len(ids)] = torch.tensor(ids)
         return out
+
+
+def _basic_clean(text):
+    """clip.simple_tokenizer.basic_clean: ftfy.fix_text, then html.unescape twice.  Without ftfy (not
+    installable offline) the Unicode NFC normalisation ftfy applies by default is kept; its mojibake repair
+    is not reproduced."""
+    try:
+        import ftfy
+
+        text = ftfy.fix_text(text)
+    except ImportError:
+        import unicodedata
+
+        text = unicodedata.normalize("NFC", text)
+    return html.unescape(html.unescape(text)).strip()
+
+
+def _whitespace_clean(text):
+    import re
+
+    return re.sub(r"\s+", " ", text).strip()
 
 
 def _bytes_to_unicode():
@@ -399,14 +488,43 @@ class _MissingTokenizer:
 
 
 def _find_checkpoint(key, clip_cache_path):
+    """`<clip_cache_path>/<name>.{pt,pth,bin}` with `/`, `@`, `:` of the model name turned into `-`
+    (e.g. `ViT-L-14.pt`, `hf_clip-patrickjohncyh-fashion-clip.bin`), or a HuggingFace snapshot folder
+    `<clip_cache_path>/<repo>/pytorch_model.bin` for `hf_clip:` names."""
     if not clip_cache_path:
         return None
-    stem = key.replace("open_clip:", "").replace("/", "-").replace("@", "-")
-    for ext in (".pt", ".pth", ".bin"):
-        p = os.path.join(clip_cache_path, stem + ext)
+    stems = [key.replace("open_clip:", "").replace("/", "-").replace("@", "-").replace(":", "-")]
+    if key.startswith("hf_clip:"):
+        repo = key[len("hf_clip:"):]
+        stems.append(repo.replace("/", "-"))
+        p = os.path.join(clip_cache_path, repo, "pytorch_model.bin")
         if os.path.exists(p):
             return p
+    for stem in stems:
+        for ext in (".pt", ".pth", ".bin"):
+            p = os.path.join(clip_cache_path, stem + ext)
+            if os.path.exists(p):
+                return p
     return None
+
+
+def read_checkpoint(path, arch):
+    """Load a checkpoint file into the OpenAI/open_clip state_dict key layout `load_state_dict` takes.
+    Accepted: a plain state_dict, a training checkpoint `{"state_dict": ...}` (optionally with `module.`
+    prefixes), a TorchScript archive (OpenAI's released `.pt` files), a HuggingFace CLIPModel state_dict."""
+    torch = _torch()
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+    except RuntimeError:
+        obj = torch.jit.load(path, map_location="cpu")
+    sd = obj if isinstance(obj, dict) else obj.state_dict()
+    if "state_dict" in sd and isinstance(sd["state_dict"], dict):
+        sd = sd["state_dict"]
+    if sd and all(k.startswith("module.") for k in sd):
+        sd = {k[len("module."):]: v for k, v in sd.items()}
+    if any(k.startswith("vision_model.") for k in sd):
+        sd = convert_hf_state_dict(sd, arch)
+    return sd
 
 
 @lru_cache(maxsize=None)
@@ -434,16 +552,15 @@ def load_clip(clip_model="ViT-B/32", use_jit=True, warmup_batch_size=1, clip_cac
     if clip_model.startswith("synthetic:"):
         model.load_state_dict(synthetic_state_dict(arch, seed=0))
     else:
+        if key.startswith("nm:"):
+            raise NotImplementedError("%r names a DeepSparse quantised ONNX export; this engine loads dense "
+                                      "state_dicts (use the open_clip checkpoint of the same architecture)" % clip_model)
         ckpt = _find_checkpoint(key, clip_cache_path)
         if ckpt is None:
             raise FileNotFoundError(
                 "no checkpoint for %r under clip_cache_path=%r (no network here); use 'synthetic:%s' for "
                 "seeded random weights" % (clip_model, clip_cache_path, clip_model))
-        sd = torch.load(ckpt, map_location="cpu")
-        sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd.state_dict()
-        if any(k.startswith("vision_model.") for k in sd):
-            sd = convert_hf_state_dict(sd, arch)
-        model.load_state_dict(sd)
+        model.load_state_dict(read_checkpoint(ckpt, arch))
     preprocess = make_preprocess(arch.image_size)
     bpe = os.path.join(clip_cache_path, "bpe_simple_vocab_16e6.txt.gz") if clip_cache_path else None
     if bpe and os.path.exists(bpe):

@@ -257,6 +257,20 @@ int b200_dedup_device(const float* d_rows, int k, int d, float threshold, uint8_
 int b200_prompt_argmax_device(const float* d_rows, int k, int d, const float* d_prompts, int n_prompts, int target,
                               uint8_t* d_flag, int device, void* stream);
 
+/* ---- dense fp32 MLP head on reconstructed rows --------------------------------
+ * Replaces the H14 NSFW detector the reference evaluates on the CPU per request:
+ * clip_retrieval/h14_nsfw_model.py:15-34 (7 Linear layers 1024-1024-2048-1024-256-128-16-1, ReLU after
+ * the first five, Dropout = identity in eval) as called by KnnService.get_unsafe_items
+ * (clip_back.py:315-319: `safety_model.predict(embeddings)`, row unsafe iff logit > 0.5).
+ * dims: [n_layers + 1] layer widths; relu: [n_layers] 0/1; weights are nn.Linear's [out, in] fp32.
+ * b200_mlp_forward_device: d_x fp32 [n, dims[0]] -> d_y fp32 [n, dims[n_layers]], asynchronous on
+ * `stream`; fp32 operands and accumulation (the reference's arithmetic class). */
+typedef struct b200_mlp b200_mlp;
+int b200_mlp_create(int n_layers, const int32_t* dims, const uint8_t* relu, int device, b200_mlp** out);
+int b200_mlp_destroy(b200_mlp* m);
+int b200_mlp_load_layer(b200_mlp* m, int layer, const float* h_weight, const float* h_bias);
+int b200_mlp_forward_device(b200_mlp* m, const float* d_x, int n, float* d_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

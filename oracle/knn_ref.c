@@ -125,3 +125,70 @@ int knn_flat_ip_f16(const uint16_t* X, int64_t n, int d, const float* Q, int nq,
   free(all); free(heaps); free(counts);
   return T;
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * IVF-Flat, inner product (FAISS IndexIVFFlat / "IVF{nlist},SQfp16" with METRIC_INNER_PRODUCT, restated):
+ * per query, (1) coarse quantiser = exhaustive inner product with the nlist centroids, keep the nprobe
+ * largest (ties to the lower list id); (2) scan the rows of those lists (stored list after list), exact
+ * fp32-accumulated inner products, k-best heap; (3) sort: score descending, ties by ascending id.
+ * FAISS parallelises IVF search over queries (OpenMP); so do the pthreads here.
+ *   X: [n, d] fp16 bits in LIST ORDER; offsets: [nlist + 1]; ids: [n] id of the row at each slot;
+ *   C: [nlist, d] fp16 bits (centroids as the index stores them); Q: [nq, d] fp32.
+ * Returns threads used. */
+typedef struct {
+  const uint16_t* X; const int64_t* offsets; const int64_t* ids; const uint16_t* C; int nlist, d;
+  const float* Q; int q_lo, q_hi, k, nprobe; float* D; int64_t* I; int64_t* probes_out;
+} ivf_job_t;
+
+static void* ivf_queries(void* arg) {
+  ivf_job_t* j = (ivf_job_t*)arg;
+  const int k = j->k, np = j->nprobe;
+  cand_t* ph = (cand_t*)malloc((size_t)np * sizeof(cand_t));
+  cand_t* h = (cand_t*)malloc((size_t)k * sizeof(cand_t));
+  for (int q = j->q_lo; q < j->q_hi; q++) {
+    const float* qv = j->Q + (size_t)q * j->d;
+    int pc = 0;
+    for (int l = 0; l < j->nlist; l++) {
+      cand_t c; c.s = dot_f16(j->C + (size_t)l * j->d, qv, j->d); c.id = l;
+      if (c.s == c.s) heap_push(ph, &pc, np, c);
+    }
+    qsort(ph, pc, sizeof(cand_t), cmp_best_first);
+    int hc = 0;
+    for (int p = 0; p < pc; p++) {
+      const int64_t l = ph[p].id;
+      if (j->probes_out) j->probes_out[(size_t)q * np + p] = l;
+      for (int64_t r = j->offsets[l]; r < j->offsets[l + 1]; r++) {
+        cand_t c; c.s = dot_f16(j->X + (size_t)r * j->d, qv, j->d); c.id = j->ids[r];
+        if (c.s == c.s) heap_push(h, &hc, k, c);
+      }
+    }
+    if (j->probes_out) for (int p = pc; p < np; p++) j->probes_out[(size_t)q * np + p] = -1;
+    qsort(h, hc, sizeof(cand_t), cmp_best_first);
+    for (int i = 0; i < k; i++) {
+      if (i < hc) { j->D[(size_t)q * k + i] = h[i].s; j->I[(size_t)q * k + i] = h[i].id; }
+      else { j->D[(size_t)q * k + i] = -FLT_MAX; j->I[(size_t)q * k + i] = -1; }
+    }
+  }
+  free(ph); free(h);
+  return NULL;
+}
+
+int knn_ivf_ip_f16(const uint16_t* X, const int64_t* offsets, const int64_t* ids, const uint16_t* C, int nlist, int d,
+                   const float* Q, int nq, int k, int nprobe, float* D, int64_t* I, int64_t* probes_out, int nthreads) {
+  int T = nthreads > 0 ? nthreads : (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (T < 1) T = 1;
+  if (T > 256) T = 256;
+  if (T > nq) T = nq > 0 ? nq : 1;
+  if (nprobe > nlist) nprobe = nlist;
+  ivf_job_t* jobs = (ivf_job_t*)malloc((size_t)T * sizeof(ivf_job_t));
+  pthread_t* th = (pthread_t*)malloc((size_t)T * sizeof(pthread_t));
+  for (int t = 0; t < T; t++) {
+    ivf_job_t j = {X, offsets, ids, C, nlist, d, Q, (int)((int64_t)nq * t / T), (int)((int64_t)nq * (t + 1) / T), k, nprobe,
+                   D, I, probes_out};
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, ivf_queries, &jobs[t]);
+  }
+  for (int t = 0; t < T; t++) pthread_join(th[t], NULL);
+  free(jobs); free(th);
+  return T;
+}

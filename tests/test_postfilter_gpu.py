@@ -100,3 +100,25 @@ def test_violence_detector_matches_einsum_argmax():
 def test_dedup_rejects_oversized_k():
     with pytest.raises(b200.B200Error):
         b200.dedup_mask(np.zeros((4097, 8), np.float32))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("n", [1, 40, 3000])
+def test_h14_nsfw_head_matches_reference_module(n):
+    """The H14 NSFW MLP (h14_nsfw_model.py:15-34, used at clip_back.py:315-319) on the GPU against the
+    reference's own nn.Sequential stack instantiated with seeded weights (fp32 on the CPU)."""
+    sd = R.h14_nsfw_state_dict(seed=3)
+    rng = np.random.default_rng(n)
+    E = (8.0 * rng.standard_normal((n, 1024))).astype(np.float32)   # spread the logits of the seeded weights
+    det = b200.H14NsfwDetector(state_dict=sd)
+    got = det.predict(E, batch_size=n)
+    ref = R.h14_nsfw_predict(sd, E)
+    assert got.shape == (n, 1) and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-5)
+    thr = float(np.median(ref)) if n > 1 else 0.5     # seeded weights: put the decision boundary inside the data
+    keep = np.nonzero(np.abs(ref[:, 0] - thr) > 1e-4)[0]   # rows not sitting on the threshold
+    unsafe = b200.get_unsafe_items(det, E, threshold=thr)
+    want = R.get_unsafe_items(sd, E, threshold=thr)
+    assert set(np.intersect1d(unsafe, keep).tolist()) == set(np.intersect1d(want, keep).tolist())
+    if n == 3000:
+        assert 0.3 * n < len(want) < 0.7 * n          # the test exercises both outcomes
