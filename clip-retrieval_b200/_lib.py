@@ -96,6 +96,13 @@ PROTOTYPES = {
     "b200_index_reconstruct_device": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "b200_topk_merge_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200_index_last_scan_ms": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "b200_topk_merge_packed_device": (_i, [_vp, _i, C.c_size_t, _i, _i, _vp, _vp, _i, _vp]),
+    "b200_sharded_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp)]),
+    "b200_sharded_destroy": (_i, [_vp]),
+    "b200_sharded_peer_mode": (_i, [_vp]),
+    "b200_sharded_search": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, _vp, _vp]),
+    "b200_nccl_comm_init_all": (_i, [_i, C.POINTER(C.c_int), C.POINTER(_vp)]),
+    "b200_nccl_comm_destroy": (_i, [_vp]),
     "b200_clip_create": (_i, [C.POINTER(ClipConfigC), _i, C.POINTER(_vp)]),
     "b200_clip_destroy": (_i, [_vp]),
     "b200_clip_load_weights": (_i, [_vp, C.POINTER(TensorViewC), _i]),

@@ -71,9 +71,11 @@ struct Cand {
 __device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
   return a.ord > b.ord || (a.ord == b.ord && a.id < b.id);
 }
+// Dg / Ig point at shard 0's [nq, k] arrays; shard g's arrays sit g * stride_d / g * stride_i BYTES further (so the
+// merge reads either [G, nq, k] arrays or an all-gathered buffer of packed per-shard blocks in place).
 __global__ void __launch_bounds__(1024)
-merge_shards_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, int G, int nq, int k, int P,
-                    float* __restrict__ D, int64_t* __restrict__ I) {
+merge_shards_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig, size_t stride_d, size_t stride_i, int G,
+                    int nq, int k, int P, float* __restrict__ D, int64_t* __restrict__ I) {
   extern __shared__ unsigned char smem_raw[];
   uint32_t* ords = reinterpret_cast<uint32_t*>(smem_raw);
   int64_t* ids = reinterpret_cast<int64_t*>(smem_raw + (size_t)P * 4 + ((P & 1) ? 4 : 0));
@@ -84,9 +86,12 @@ merge_shards_kernel(const float* __restrict__ Dg, const int64_t* __restrict__ Ig
     int64_t id = INT64_MAX;
     if (i < M) {
       const int g = i / k, j = i % k;
-      const int64_t src = ((int64_t)g * nq + q) * k + j;
-      const int64_t gid = Ig[src];
-      if (gid >= 0) { o = f32_to_ordered(Dg[src]); id = gid; }
+      const int64_t src = (int64_t)q * k + j;
+      const int64_t gid = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(Ig) + (size_t)g * stride_i)[src];
+      if (gid >= 0) {
+        o = f32_to_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(Dg) + (size_t)g * stride_d)[src]);
+        id = gid;
+      }
     }
     ords[i] = o;
     ids[i] = id;
@@ -156,6 +161,26 @@ static int search_device_impl(b200_index* idx, const float* d_q, int nq, int k, 
     B200_LAUNCH_OK();
   }
   return B200_OK;
+}
+
+static int merge_launch(const float* d_Dg, const int64_t* d_Ig, size_t stride_d, size_t stride_i, int G, int nq, int k,
+                        float* d_D, int64_t* d_I, cudaStream_t st) {
+  int P = 2;
+  while (P < G * k) P <<= 1;
+  const size_t smem = (size_t)P * 4 + ((P & 1) ? 4 : 0) + (size_t)P * 8;
+  B200_CHECK(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "merge: G*k=%d exceeds 16384 candidates per query", G * k);
+  if (smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_shards_kernel<<<nq, 1024, smem, st>>>(d_Dg, d_Ig, stride_d, stride_i, G, nq, k, P, d_D, d_I);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+// packed per-shard blocks [I int64 nq*k | D f32 nq*k | padding], `stride` bytes apart (sharded.cu, sharded.py)
+int merge_packed_launch(const void* d_gathered, int G, size_t stride, int nq, int k, float* d_D, int64_t* d_I,
+                        cudaStream_t st) {
+  const char* base = (const char*)d_gathered;
+  return merge_launch((const float*)(base + (size_t)nq * k * 8), (const int64_t*)base, stride, stride, G, nq, k, d_D, d_I, st);
 }
 
 }  // namespace b200
@@ -430,16 +455,18 @@ int b200_topk_merge_device(const float* d_Dg, const int64_t* d_Ig, int G, int nq
                            int device, void* stream) {
   B200_CHECK(d_Dg && d_Ig && d_D && d_I && G >= 1 && nq >= 0 && k >= 1, B200_ERR_INVALID, "merge: bad argument");
   if (nq == 0) return B200_OK;
-  int P = 2;
-  while (P < G * k) P <<= 1;
-  const size_t smem = (size_t)P * 4 + ((P & 1) ? 4 : 0) + (size_t)P * 8;
-  B200_CHECK(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "merge: G*k=%d exceeds 8192", G * k);
   DeviceGuard g(device);
-  if (smem > 48 * 1024)
-    B200_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_shards_kernel<<<nq, 1024, smem, (cudaStream_t)stream>>>(d_Dg, d_Ig, G, nq, k, P, d_D, d_I);
-  B200_LAUNCH_OK();
-  return B200_OK;
+  return merge_launch(d_Dg, d_Ig, (size_t)nq * k * 4, (size_t)nq * k * 8, G, nq, k, d_D, d_I, (cudaStream_t)stream);
+}
+
+int b200_topk_merge_packed_device(const void* d_gathered, int G, size_t shard_stride_bytes, int nq, int k, float* d_D,
+                                  int64_t* d_I, int device, void* stream) {
+  B200_CHECK(d_gathered && d_D && d_I && G >= 1 && nq >= 0 && k >= 1, B200_ERR_INVALID, "merge_packed: bad argument");
+  B200_CHECK(shard_stride_bytes >= (size_t)nq * k * 12 && shard_stride_bytes % 8 == 0, B200_ERR_INVALID,
+             "merge_packed: shard stride %zu too small for nq=%d k=%d or not a multiple of 8", shard_stride_bytes, nq, k);
+  if (nq == 0) return B200_OK;
+  DeviceGuard g(device);
+  return merge_packed_launch(d_gathered, G, shard_stride_bytes, nq, k, d_D, d_I, (cudaStream_t)stream);
 }
 
 int b200_index_last_scan_ms(const b200_index* idx, float* ms, int* launches) {

@@ -35,6 +35,9 @@ class SynthSpec:
         return _lib.SynthSpecC(self.seed, 1 if self.clustered else 0, self.centroid_seed, self.nlist, self.cw, self.nw)
 
 
+MAX_K = 8192   # results per query a single search supports (per-warp candidate lists live in shared memory)
+
+
 def _torch():
     import torch  # device memory / streams only
 
@@ -137,6 +140,8 @@ class _IndexBase:
     # ---- searching (host buffers: what the reference calls) ----
     def search(self, x, k):
         x = _as_query(x, self.d)
+        if int(k) > MAX_K:
+            raise ValueError("search: k=%d exceeds the supported maximum of %d results per query" % (k, MAX_K))
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
@@ -145,6 +150,8 @@ class _IndexBase:
 
     def search_and_reconstruct(self, x, k):
         x = _as_query(x, self.d)
+        if int(k) > MAX_K:
+            raise ValueError("search: k=%d exceeds the supported maximum of %d results per query" % (k, MAX_K))
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
@@ -156,24 +163,33 @@ class _IndexBase:
         return D, I, R
 
     # ---- searching (device buffers, asynchronous on the current stream) ----
-    def search_device(self, q, k, reconstruct=False):
-        """q: CUDA float32 torch tensor [nq, d].  Returns (D, I[, R]) CUDA tensors."""
+    def search_device(self, q, k, reconstruct=False, out=None):
+        """q: CUDA float32 torch tensor [nq, d].  Returns (D, I[, R]) CUDA tensors.  `out=(D, I)` writes the result
+        into caller-provided contiguous [nq, k] float32 / int64 tensors (e.g. views of a collective's send buffer).
+        The C entry serialises concurrent calls on the handle (mutex + stream-ordered scratch reuse)."""
         torch = _torch()
         if not (q.is_cuda and q.dtype == torch.float32 and q.dim() == 2 and q.shape[1] == self.d):
             raise ValueError("search_device: q must be CUDA float32 [nq, %d]" % self.d)
+        if int(k) > MAX_K:
+            raise ValueError("search: k=%d exceeds the supported maximum of %d results per query" % (k, MAX_K))
         q = q.contiguous()
         nq = q.shape[0]
-        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        if out is None:
+            D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        else:
+            D, I = out
+            if not (D.is_contiguous() and I.is_contiguous() and D.dtype == torch.float32 and I.dtype == torch.int64
+                    and tuple(D.shape) == (nq, k) and tuple(I.shape) == (nq, k) and D.device == q.device and I.device == q.device):
+                raise ValueError("search_device: out must be contiguous (float32 [nq,k], int64 [nq,k]) on the query's device")
         R = torch.empty((nq, k, self.d), dtype=torch.float32, device=q.device) if reconstruct else None
         st = torch.cuda.current_stream(q.device).cuda_stream
-        with self._lock:
-            check(
-                lib.b200_index_search_device(
-                    self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), R.data_ptr() if reconstruct else None, st
-                ),
-                "search_device",
-            )
+        check(
+            lib.b200_index_search_device(
+                self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), R.data_ptr() if reconstruct else None, st
+            ),
+            "search_device",
+        )
         return (D, I, R) if reconstruct else (D, I)
 
     def set_tensor_scan(self, on):
@@ -351,3 +367,15 @@ def build_ivf_index(rows, nlist, niter=10, seed=1234, nprobe=1, device=0):
     idx.add(rows)
     idx.nprobe = nprobe
     return idx
+
+
+def merge_packed_results(gathered, G, stride_bytes, nq, k):
+    """Merge G packed per-shard blocks ([I int64 nq*k | D f32 nq*k], `stride_bytes` apart) read in place from
+    `gathered` (a CUDA uint8 tensor: the receive buffer of the all-gather) into the global top-k [nq, k]."""
+    torch = _torch()
+    D = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+    st = torch.cuda.current_stream(gathered.device).cuda_stream
+    check(lib.b200_topk_merge_packed_device(gathered.data_ptr(), int(G), C.c_size_t(int(stride_bytes)), int(nq), int(k),
+                                            D.data_ptr(), I.data_ptr(), gathered.device.index or 0, st), "topk_merge_packed")
+    return D, I

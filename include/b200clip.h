@@ -132,6 +132,30 @@ int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t
  * per-shard candidates): d_Dg/d_Ig are [G, nq, k]; outputs [nq, k]. */
 int b200_topk_merge_device(const float* d_Dg, const int64_t* d_Ig, int G, int nq, int k,
                            float* d_D, int64_t* d_I, int device, void* stream);
+/* Same merge reading G packed per-shard blocks in place — block g at d_gathered + g * shard_stride_bytes holds
+ * [I int64 nq*k | D fp32 nq*k] — i.e. the receive buffer of ONE all-gather whose send buffer is the block a shard's
+ * b200_index_search_device wrote (d_I = block, d_D = block + nq*k*8): no pack/unpack kernels around the collective. */
+int b200_topk_merge_packed_device(const void* d_gathered, int G, size_t shard_stride_bytes, int nq, int k,
+                                  float* d_D, int64_t* d_I, int device, void* stream);
+
+/* Range-sharded search across the GPUs of one box from ONE host thread: shard g is a
+ * b200_index on its own device holding rows [lo_g, hi_g) with id_base = lo_g; queries are replicated, every shard
+ * searches on its own stream, ONE exchange of the per-shard candidates, a device merge; h_D/h_I receive the global
+ * top-k.  comms == NULL: the exchange is the search epilogue itself — each shard's last kernel stores its
+ * candidate block into the root device's buffer through an NVLink peer mapping (staged copies when a device pair has
+ * no peer access).  comms != NULL: `nshards` ncclComm_t (comms[g] = rank g, bound to shard g's device): one
+ * ncclAllGather group, the one-process-per-GPU protocol of sharded.py; NCCL is resolved with dlopen at run time.
+ * The reference has no sharded search (one CPU FAISS index per process, clip_back.py:781-782); the query contract is
+ * index.search (clip_back.py:362, clip_filter.py:55). */
+typedef struct b200_sharded b200_sharded;
+int b200_sharded_create(b200_index* const* shards, int nshards, b200_sharded** out);
+int b200_sharded_destroy(b200_sharded* h);
+int b200_sharded_peer_mode(const b200_sharded* h);   /* 1: candidates travel as peer stores; 0: staged copies */
+int b200_sharded_search(b200_sharded* h, void* const* comms, const float* h_q, int nq, int k, float* h_D, int64_t* h_I);
+/* ncclCommInitAll / ncclCommDestroy through the same run-time binding (hosts without their own NCCL bootstrap). */
+int b200_nccl_comm_init_all(int n, const int* devices, void** comms_out);
+int b200_nccl_comm_destroy(void* comm);
+
 /* Duration in milliseconds (CUDA events on the launching stream) of the row-scan kernels of the
  * last search call on this handle, and how many such kernels it launched.  bench.py uses it for
  * the roofline of the dominant kernel. */

@@ -285,3 +285,29 @@ def test_range_search_matches_oracle(b200):
             ids = I[lims[q]:lims[q + 1]]
             assert np.all(np.diff(ids) > 0)
             np.testing.assert_allclose(D[lims[q]:lims[q + 1]], S64[q, ids], atol=TOL)
+
+
+def test_load_index_on_writer_format_shards(b200, tmp_path):
+    """a10: `load_index(folder)` (clip_back.py:589-596 counterpart) on fp16 shards named as the reference writer
+    names them (`img_emb_{id:0{w}d}.npy`, writer.py:22,67-87); rows land in sorted-file order = global id order."""
+    d, k = 512, 10
+    X = synth_ref.rows_f16(3000, d)
+    parts = [X[:1000], X[1000:1100], X[1100:]]
+    folder = tmp_path / "img_emb"
+    folder.mkdir()
+    for i, p in enumerate(parts):
+        np.save(str(folder / ("img_emb_%02d.npy" % i)), p)
+    (folder / "ignored.txt").write_text("x")
+    idx = b200.load_index(str(folder), enable_faiss_memory_mapping=True)
+    assert idx.ntotal == 3000 and idx.d == d
+    Q = _queries(4, d)
+    D, I, R = idx.search_and_reconstruct(Q, k)
+    ok, msg, strict = knn_ref.check_topk(D, I, knn_ref.scores_f64(X, Q), k, tol=TOL)
+    assert ok and strict == 4, msg
+    assert np.array_equal(R, knn_ref.reconstruct(X, I))
+    one = b200.load_index(str(folder / "img_emb_01.npy"))
+    assert one.ntotal == 100
+    with pytest.raises(ValueError):
+        b200.load_index(str(tmp_path))                    # no shard there
+    with pytest.raises(ValueError):
+        idx.search(Q, 9000)                               # k above the supported maximum: a clear error, not a CUDA one
