@@ -232,3 +232,30 @@ def test_index_contract_through_reference_knn_search():
     assert np.all(np.diff(np.array(dist)) <= 0) and set(int(i) for i in ind[:2]) == {3, 7}
     dist2, ind2 = ns["knn_search"](svc, q, "image", 40, res, True, False, False)    # with dedup
     assert len(ind2) == 29 and int(ind2[0]) == 3 and 7 not in [int(i) for i in ind2]
+
+
+def test_ivf_c_restatement_matches_numpy_oracle():
+    """oracle/knn_ref.c `knn_ivf_ip_f16` (the CPU baseline of BASELINE configs[3]/[4]) against the numpy IVF oracle:
+    same probes, same ids, same scores, -1 padding when the probed lists hold fewer than k rows."""
+    from oracle import knn_c
+
+    n, d, nlist, k = 6000, 64, 41, 25
+    kw = dict(seed=99, clustered=True, centroid_seed=7, nlist=nlist)
+    X = synth_ref.rows_f16(n, d, **kw)
+    C16 = synth_ref.centroids_f32(nlist, d, 7).astype(np.float16)
+    Q = synth_ref.rows_f32(7, d, seed=5, clustered=True, centroid_seed=7, nlist=nlist)
+    assign = knn_ref.ivf_assign(X, C16)
+    Xl, off, ids = knn_c.ivf_layout(X, assign, nlist)
+    assert off[-1] == n and np.array_equal(np.sort(ids), np.arange(n))
+    for nprobe in (1, 3, nlist):
+        D, I, threads, probes = knn_c.ivf_search(Xl, off, ids, C16, Q, k, nprobe, id_base=1000, return_probes=True)
+        Do, Io, po = knn_ref.ivf_search(X, assign, C16, Q, k, nprobe, id_base=1000)
+        assert threads >= 1 and np.array_equal(probes, po[:, :nprobe])
+        assert np.array_equal(I, Io)
+        np.testing.assert_allclose(D, Do, atol=2e-6)
+    # nprobe = nlist is the exhaustive search
+    Df, If = knn_ref.flat_search(X, Q, k, id_base=1000)
+    assert np.array_equal(I, If)
+    # tiny lists: fewer than k rows in the probed list -> -1 / -FLT_MAX tail
+    D, I, _ = knn_c.ivf_search(Xl[:off[1]], off[:2], ids[:off[1]], C16[:1], Q, max(k, int(off[1]) + 3), 1)
+    assert (I[:, off[1]:] == -1).all() and (D[:, off[1]:] == knn_ref.NEG).all()
