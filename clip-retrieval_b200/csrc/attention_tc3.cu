@@ -1,0 +1,513 @@
+// K4 on tcgen05, third generation (production attention for head dim 64, T <= 264: every CLIP tower at 224 px
+// except H/14's vision tower).  Same skeleton as attention_tc2.cu — two query tiles in flight, S and O in TMEM, P
+// through swizzled shared memory, V as an MN-major operand — with the three things its profile asked for
+// (profiles/r01f: tensor 14 %, XU 30 %, two TMEM read passes ~ 64 B/clk/SM):
+//
+//  1. ONE pass over the scores.  Softmax is shift invariant, and fp32 / bf16 carry the same relative precision at
+//     every magnitude, so the subtracted value need not be the row maximum: any m with  max_j s_ij <= m  cannot
+//     overflow, and as long as m - max_j s_ij stays below ~64 (log2 units) every term that matters is far from the
+//     flush-to-zero limit.  m_i = |q_i| * max_j |k_j| * scale (Cauchy-Schwarz) is such a bound, costs one 64-term
+//     norm per row, and is known BEFORE the scores exist.  The pass also tracks the true row maximum; if a row's
+//     slack exceeds 64 the warp repeats the pass with the exact maximum (the scores are still in TMEM): results are
+//     those of the two-pass softmax in every case, the second read happens only for pathological rows.
+//  2. T = 257 = 2 * 128 + 1 is two tensor-core tiles plus ONE row: the leftover rows (T mod 128 <= 8) are computed by
+//     a dedicated warp on the FMA pipe straight from the K / V tiles in shared memory (exact two-pass softmax in
+//     registers), instead of a third 128-row tile that is 99 % padding.
+//  3. tcgen05.ld of score chunk c+1 is in flight while chunk c is exponentiated (two register buffers).
+// Per-sample 3-D tensor maps (rows >= T of a box are zero-filled) keep a sample's boxes from reading its neighbour.
+//
+//   warp 8      TMA: K, V rows of the head (128-row boxes) once per (sample, head), Q tile per 128 query rows.
+//   warp 9      tcgen05.mma issuer: S(t) = Q K^T, O(t) = P V; order S(t), PV(t-1), S(t+1), PV(t), ...
+//   warp 10     per head: max_j |k_j| for the softmax bound, and the leftover query rows on the FMA pipe.
+//   warps 0..3  softmax group 0 (even tiles), warps 4..7 group 1 (odd tiles): thread = query row.
+#include "embed_kernels.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int A3_HD = 64;
+constexpr int A3_MAXT = 264;                      // 256 keys on the tensor core + up to 8 extra keys
+constexpr int A3_Q_BYTES = 128 * 128;             // 16 KB
+constexpr int A3_KV_MAIN = 2 * 128 * 128;         // 256 rows x 128 B
+constexpr int A3_P_BYTES = 4 * 128 * 128;         // 4 key blocks of [128 rows x 64 keys] per group
+constexpr int A3_SMEM = A3_Q_BYTES + 2 * A3_KV_MAIN + 2 * A3_P_BYTES + 512 + 1024;
+constexpr int A3_THREADS = 352;
+constexpr float A3_MAX_SLACK = 64.0f;             // log2 units; above it the pass is repeated with the exact maximum
+
+// 8 consecutive bf16 of a swizzled K/V row in shared memory -> fp32
+__device__ __forceinline__ void a3_unpack8(const uint4& u, float* f) {
+  const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+  f[0] = a0.x; f[1] = a0.y; f[2] = a1.x; f[3] = a1.y; f[4] = a2.x; f[5] = a2.y; f[6] = a3.x; f[7] = a3.y;
+}
+
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat16* __restrict__ qkv,
+                     __nv_bfloat16* __restrict__ out, int B, int T, int heads, int w, float scale_log2e, int causal) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = base;
+  uint8_t* sK = sQ + A3_Q_BYTES;               // rows 0..255
+  uint8_t* sV = sK + A3_KV_MAIN;               // rows 0..255
+  uint8_t* sP = sV + A3_KV_MAIN;               // [2 groups][4 key blocks][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A3_P_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_free = bars + 3;    // MMA commit (last S of the head) + warp 10
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_free = bars + 5;    // MMA commit (last P.V of the head) + warp 10
+  uint64_t* s_full = bars + 6;    // [2]
+  uint64_t* p_full = bars + 8;    // [2]
+  uint64_t* o_full = bars + 10;   // [2]
+  uint64_t* buf_free = bars + 12; // [2]
+  uint64_t* kn_full = bars + 14;  // [4]  max |k| of head `it` published in s_kn[it & 3]
+  float* s_kn = reinterpret_cast<float*>(bars + 18);   // [4]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_kn + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int keys_main = T < 256 ? (T + 15) / 16 * 16 : 256;  // keys on the tensor core (multiple of 16)
+  const int extra = T > 256 ? T - 256 : 0;                    // keys handled on the FMA pipe
+  const int kv_boxes = (keys_main + 127) / 128;
+  // query rows: full/partial 128-row tiles on the tensor core, a leftover of <= 8 rows (after at least one full
+  // tile) on the FMA pipe
+  const int n_full = T / 128, rem = T - n_full * 128;
+  const bool tail_rows = rem > 0 && rem <= 8 && n_full >= 1;
+  const int q_tiles = tail_rows ? n_full : (T + 127) / 128;
+  const int fma_rows = tail_rows ? rem : 0;
+  const int items = B * heads;
+
+  if (warp == 8 && lane == 0) ptx::prefetch_tensormap(&tm3);
+  if (warp == 9) {
+    if (lane == 0) {
+      ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
+      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, 2);
+      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 2);
+      for (int i = 0; i < 2; i++) {
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&p_full[i], 4);
+        ptx::mbar_init(&o_full[i], 1);
+        ptx::mbar_init(&buf_free[i], 4);
+      }
+      for (int i = 0; i < 4; i++) ptx::mbar_init(&kn_full[i], 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(s_tmem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      const uint32_t kv_bytes = (uint32_t)(kv_boxes * 128 * 128);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+        const int b = item / heads, h = item - b * heads;
+        ptx::mbar_wait(k_free, (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(k_full, kv_bytes);
+        for (int i = 0; i < kv_boxes; i++) ptx::tma_load_3d(sK + i * 128 * 128, &tm3, k_full, w + h * A3_HD, i * 128, b);
+        for (int mt = 0; mt < q_tiles; mt++, tc++) {
+          ptx::mbar_wait(q_empty, (tc & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(q_full, A3_Q_BYTES);
+          ptx::tma_load_3d(sQ, &tm3, q_full, h * A3_HD, mt * 128, b);
+          if (mt == 0) {
+            ptx::mbar_wait(v_free, (it & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(v_full, kv_bytes);
+            for (int i = 0; i < kv_boxes; i++)
+              ptx::tma_load_3d(sV + i * 128 * 128, &tm3, v_full, 2 * w + h * A3_HD, i * 128, b);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_f16(128, keys_main, true);
+      const uint32_t idesc_o = ptx::umma_idesc_f16(128, A3_HD, true) | (1u << 16);  // B (= V) is MN-major
+      uint32_t it = 0, tc = 0;
+      bool have_prev = false;
+      uint32_t prev_tc = 0, prev_it = 0;
+      bool prev_last = false, prev_first = false;
+      auto issue_pv = [&](uint32_t ptc, bool first_of_item, bool last_of_item, uint32_t pit) {
+        const int pb = ptc & 1;
+        if (first_of_item) ptx::mbar_wait(v_full, pit & 1);
+        ptx::mbar_wait(&p_full[pb], (ptc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint8_t* sPg = sP + pb * A3_P_BYTES;
+        for (int ks = 0; ks < keys_main / 16; ks++) {
+          const uint64_t dp = ptx::umma_desc_k_sw128(ptx::smem_u32(sPg + (ks >> 2) * (128 * 128))) + (uint64_t)((ks & 3) * 2);
+          const uint64_t dv = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + ks * 16 * 128));  // 16 keys = 2 swizzle atoms
+          ptx::umma_f16(tmem_base + pb * 256, dp, dv, idesc_o, ks != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&o_full[pb]);
+        if (last_of_item) ptx::umma_commit(v_free);
+      };
+      for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+        for (int mt = 0; mt < q_tiles; mt++, tc++) {
+          const int bsel = tc & 1;
+          if (mt == 0) ptx::mbar_wait(k_full, it & 1);
+          ptx::mbar_wait(q_full, tc & 1);
+          ptx::mbar_wait(&buf_free[bsel], ((tc >> 1) & 1) ^ 1);   // O(tc-2) has been read out of this buffer
+          ptx::tc_fence_after();
+          const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
+          const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
+#pragma unroll
+          for (int k = 0; k < A3_HD / 16; k++)
+            ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+          ptx::umma_commit(q_empty);
+          ptx::umma_commit(&s_full[bsel]);
+          if (mt == q_tiles - 1) ptx::umma_commit(k_free);
+          if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
+          have_prev = true;
+          prev_tc = tc;
+          prev_first = mt == 0;
+          prev_last = mt == q_tiles - 1;
+          prev_it = it;
+        }
+      }
+      if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ---------------- per head: max |k| for the softmax bound; leftover query rows on the FMA pipe ----------------
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+      const int b = item / heads, h = item - b * heads;
+      ptx::mbar_wait(k_full, it & 1);
+      // max_j |k_j|^2 over the keys of this head: main keys from shared memory (zero rows past T add nothing),
+      // extra keys (>= 256) from the qkv buffer
+      float kn2 = 0.f;
+      for (int j = lane; j < keys_main; j += 32) {
+        const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          float f[8];
+          a3_unpack8(*reinterpret_cast<const uint4*>(row + c * 16), f);   // chunk order is irrelevant for a norm
+#pragma unroll
+          for (int e = 0; e < 8; e++) acc = fmaf(f[e], f[e], acc);
+        }
+        kn2 = fmaxf(kn2, acc);
+      }
+      for (int e = lane; e < extra; e += 32) {
+        const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + 256 + e) * 3 * w + w + (size_t)h * A3_HD);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          float f[8];
+          a3_unpack8(__ldg(kp + c), f);
+#pragma unroll
+          for (int e2 = 0; e2 < 8; e2++) acc = fmaf(f[e2], f[e2], acc);
+        }
+        kn2 = fmaxf(kn2, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
+      if (lane == 0) {
+        s_kn[it & 3] = sqrtf(kn2) * 1.0001f + 1e-30f;   // rounding of the norms must not turn the bound into a non-bound
+        ptx::mbar_arrive(&kn_full[it & 3]);              // release semantics: s_kn is visible to the waiters
+      }
+      if (fma_rows > 0) {
+        ptx::mbar_wait(v_full, it & 1);
+        for (int fr = 0; fr < fma_rows; fr++) {
+          const int qrow = n_full * 128 + fr;
+          const int kmax = causal ? qrow : T - 1;           // last visible key
+          float qf[A3_HD];
+          const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + qrow) * 3 * w + (size_t)h * A3_HD);
+#pragma unroll
+          for (int c = 0; c < 8; c++) a3_unpack8(__ldg(qp + c), qf + c * 8);
+          // scores of keys lane, lane + 32, ... (9 per lane cover T <= 264 + slack)
+          float s[9];
+          float m = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            const int j = i * 32 + lane;
+            float acc = -INFINITY;
+            if (j <= kmax) {
+              acc = 0.f;
+              if (j < 256) {
+                const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                  float f[8];
+                  a3_unpack8(*reinterpret_cast<const uint4*>(row + ((c ^ (j & 7)) * 16)), f);
+#pragma unroll
+                  for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
+                }
+              } else {
+                const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                  float f[8];
+                  a3_unpack8(__ldg(kp + c), f);
+#pragma unroll
+                  for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
+                }
+              }
+            }
+            s[i] = acc;
+            m = fmaxf(m, acc);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          const float mb = m * scale_log2e;
+          float l = 0.f;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            float p;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[i], scale_log2e, -mb)));
+            p = s[i] == -INFINITY ? 0.f : p;
+            // P is rounded to bf16 before it multiplies V, as on the tensor-core rows; the row sum uses the fp32 value
+            s[i] = __bfloat162float(__float2bfloat16_rn(p));
+            l += p;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+          // O[2 * lane, 2 * lane + 1] = sum_j p_j v_j
+          float o0 = 0.f, o1 = 0.f;
+          const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            const int jend = min(32, kmax + 1 - i * 32);
+            for (int src = 0; src < jend; src++) {
+              const float pj = __shfl_sync(0xffffffffu, s[i], src);
+              const int j = i * 32 + src;
+              uint32_t v2;
+              if (j < 256) {
+                const uint8_t* row = sV + (j >> 7) * (128 * 128) + (j & 127) * 128;
+                v2 = *reinterpret_cast<const uint32_t*>(row + ((chunk ^ (j & 7)) * 16) + within);
+              } else {
+                v2 = __ldg(reinterpret_cast<const uint32_t*>(qkv + ((size_t)b * T + j) * 3 * w + 2 * w + (size_t)h * A3_HD) + lane);
+              }
+              const float2 vv = unpack_bf16x2(v2);
+              o0 = fmaf(pj, vv.x, o0);
+              o1 = fmaf(pj, vv.y, o1);
+            }
+          }
+          const float inv = 1.0f / l;
+          *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + qrow) * w + (size_t)h * A3_HD + 2 * lane) =
+              pack_bf16x2(o0 * inv, o1 * inv);
+        }
+      } else {
+        // no leftover rows: V is not read here, but the release barrier still counts this warp
+        ptx::mbar_wait(v_full, it & 1);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(k_free);
+        ptx::mbar_arrive(v_free);
+      }
+    }
+  } else {
+    // ---------------- softmax groups ----------------
+    const int grp = warp >> 2;                     // 0: even tiles, 1: odd tiles
+    const int q4 = warp & 3;                       // TMEM lane quarter
+    const int r = q4 * 32 + lane;                  // row inside the tile
+    const uint32_t tbase = tmem_base + grp * 256 + ((uint32_t)(q4 * 32) << 16);
+    uint8_t* sPg = sP + grp * A3_P_BYTES;
+    const int chunks = (keys_main + 31) / 32;
+    uint32_t tc = 0, it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+      const int b = item / heads, h = item - b * heads;
+      for (int mt = 0; mt < q_tiles; mt++, tc++) {
+        if ((int)(tc & 1) != grp) continue;
+        const uint32_t n = tc >> 1;
+        const int qrow = mt * 128 + r;
+        const int kmax = causal ? (qrow < T ? qrow : T - 1) : T - 1;   // last visible key
+        // ---- before the scores exist: |q|, the extra keys' scores (FMA pipe), the bound m ----
+        float se[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) se[e] = -INFINITY;
+        float qn2 = 0.f;
+        {
+          float qf[A3_HD];
+          const int qr = qrow < T ? qrow : T - 1;
+          const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + qr) * 3 * w + (size_t)h * A3_HD);
+#pragma unroll
+          for (int c = 0; c < 8; c++) a3_unpack8(qp[c], qf + c * 8);
+#pragma unroll
+          for (int c = 0; c < A3_HD; c++) qn2 = fmaf(qf[c], qf[c], qn2);
+          for (int e = 0; e < extra; e++) {
+            const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + 256 + e) * 3 * w + w + (size_t)h * A3_HD);
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              float f[8];
+              a3_unpack8(__ldg(kp + c), f);
+#pragma unroll
+              for (int e2 = 0; e2 < 8; e2++) acc = fmaf(qf[c * 8 + e2], f[e2], acc);
+            }
+#pragma unroll
+            for (int ee = 0; ee < 8; ee++)
+              if (ee == e) se[ee] = (256 + e <= kmax) ? acc : -INFINITY;
+          }
+        }
+        ptx::mbar_wait(&kn_full[it & 3], (it >> 2) & 1);
+        const float kn = *reinterpret_cast<volatile float*>(&s_kn[it & 3]);
+        float mb = sqrtf(qn2) * 1.0001f * kn * scale_log2e;      // >= every score of this row, in log2 units
+        ptx::mbar_wait(&s_full[grp], n & 1);
+        ptx::tc_fence_after();
+
+        float l, tmax;
+        float pe[8];
+        // one pass: exponentials against the bound, row sum, true maximum, P -> swizzled K-major tile of this group
+        auto pass = [&](const float mbv) {
+          float l0 = 0.f, l1 = 0.f, t0 = -INFINITY, t1 = -INFINITY;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_32x32b_x32(tbase, va);
+          ptx::tmem_ld_wait();
+          auto chunk_fn = [&](const uint32_t (&v)[32], const int c) {
+            const int lim = kmax - c * 32;
+            uint32_t pk[16];
+            if (lim >= 31) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float s0 = __uint_as_float(v[j]), s1 = __uint_as_float(v[j + 1]);
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mbv)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mbv)));
+                t0 = fmaxf(t0, s0);
+                t1 = fmaxf(t1, s1);
+                l0 += p0;
+                l1 += p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float s0 = j <= lim ? __uint_as_float(v[j]) : -INFINITY;
+                const float s1 = j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY;
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mbv)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mbv)));
+                p0 = j <= lim ? p0 : 0.f;
+                p1 = j + 1 <= lim ? p1 : 0.f;
+                t0 = fmaxf(t0, s0);
+                t1 = fmaxf(t1, s1);
+                l0 += p0;
+                l1 += p1;
+                pk[j >> 1] = pack_bf16x2(p0, p1);
+              }
+            }
+            uint8_t* blk = sPg + (c >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
+              *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
+            }
+          };
+#pragma unroll 1
+          for (int c = 0; c < chunks; c += 2) {
+            if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);   // in flight while chunk c is processed
+            chunk_fn(va, c);
+            ptx::tmem_ld_wait();
+            if (c + 1 < chunks) {
+              if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
+              chunk_fn(vb, c + 1);
+              ptx::tmem_ld_wait();
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            float p;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(se[e], scale_log2e, -mbv)));
+            pe[e] = se[e] == -INFINITY ? 0.f : p;
+            l0 += pe[e];
+            t0 = fmaxf(t0, se[e]);
+          }
+          l = l0 + l1;
+          tmax = fmaxf(t0, t1);
+        };
+        pass(mb);
+        // the bound is safe against overflow by construction; if it sits too far above the true maximum of some
+        // row of this warp, redo the pass with exact maxima (S is still in TMEM, P is simply rewritten)
+        const float exact = tmax * scale_log2e;
+        if (__any_sync(0xffffffffu, (mb - exact > A3_MAX_SLACK) && tmax != -INFINITY)) {
+          mb = tmax == -INFINITY ? mb : exact;
+          pass(mb);
+        }
+        ptx::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
+        // output: O from TMEM (+ the extra keys' p_e * v_e), * 1/l, bf16
+        ptx::mbar_wait(&o_full[grp], n & 1);
+        ptx::tc_fence_after();
+        uint32_t o0[32], o1[32];
+        ptx::tmem_ld_32x32b_x32(tbase, o0);
+        ptx::tmem_ld_32x32b_x32(tbase + 32, o1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&buf_free[grp]);
+        if (qrow < T) {
+          float of[A3_HD];
+#pragma unroll
+          for (int j = 0; j < 32; j++) { of[j] = __uint_as_float(o0[j]); of[32 + j] = __uint_as_float(o1[j]); }
+          for (int e = 0; e < extra; e++) {
+            float p = 0.f;
+#pragma unroll
+            for (int ee = 0; ee < 8; ee++) if (ee == e) p = pe[ee];
+            p = __bfloat162float(__float2bfloat16_rn(p));   // same rounding as the P that went through the tensor core
+            const uint4* vp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + 256 + e) * 3 * w + 2 * w + (size_t)h * A3_HD);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              float f[8];
+              a3_unpack8(__ldg(vp + c), f);
+#pragma unroll
+              for (int e2 = 0; e2 < 8; e2++) of[c * 8 + e2] = fmaf(p, f[e2], of[c * 8 + e2]);
+            }
+          }
+          const float inv = 1.0f / l;
+          __nv_bfloat16* op = out + ((size_t)b * T + qrow) * w + (size_t)h * A3_HD;
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            uint4 a;
+            a.x = pack_bf16x2(of[g * 8 + 0] * inv, of[g * 8 + 1] * inv);
+            a.y = pack_bf16x2(of[g * 8 + 2] * inv, of[g * 8 + 3] * inv);
+            a.z = pack_bf16x2(of[g * 8 + 4] * inv, of[g * 8 + 5] * inv);
+            a.w = pack_bf16x2(of[g * 8 + 6] * inv, of[g * 8 + 7] * inv);
+            *reinterpret_cast<uint4*>(op + g * 8) = a;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+bool attention_tc3_supported(int T, int heads, int w) {
+  return heads > 0 && w % heads == 0 && w / heads == A3_HD && T >= 1 && T <= A3_MAXT;
+}
+
+int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
+                  int causal, int sms, cudaStream_t st) {
+  B200_CHECK(attention_tc3_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc3: unsupported shape T=%d hd=%d", T,
+             heads ? w / heads : 0);
+  if (B == 0) return B200_OK;
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!(configured.load() >> (dev & 63) & 1ull)) {
+    B200_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM));
+    configured.fetch_or(1ull << (dev & 63));
+  }
+  const float scale_log2e = (1.0f / sqrtf((float)A3_HD)) * 1.4426950408889634f;
+  const int items = B * heads;
+  const int grid = items < sms ? items : sms;
+  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, B, T, heads, w, scale_log2e, causal);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+}  // namespace b200

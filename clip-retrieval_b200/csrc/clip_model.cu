@@ -16,6 +16,7 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -42,6 +43,7 @@ struct Tower {
   int Tp = 0;
   __nv_bfloat16* vt = nullptr;
   CUtensorMap tm_qk, tm_vt;
+  CUtensorMap tm_qkv3;   // per-sample 3-D map over qkv [max_batch, T, 3w] (attention_tc3.cu)
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
   __nv_bfloat16* proj = nullptr;             // [width, D]
 };
@@ -80,6 +82,7 @@ struct b200_clip {
   bool act_used = false;
   // timing
   bool profiling = false;
+  int attn_gen = 3;            // 3: attention_tc3.cu (single score pass); 2: attention_tc2.cu (B200_ATTN_GEN, A/B runs)
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
   bool attn_v_direct = true;   // P.V reads V from the qkv buffer as an MN-major operand (no V^T copy)
   struct Span { int cls; cudaEvent_t a, b; };
@@ -147,6 +150,7 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
     B200_CUDA(cudaMemset(t->vt, 0, vt_rows * t->Tp * 2));  // key padding stays zero (0 * garbage would be NaN)
     B200_TRY(make_tmap_2d(&t->tm_qk, t->qkv, 1, rows, 3 * (size_t)w, 3 * (size_t)w, 128, 64));
     B200_TRY(make_tmap_2d(&t->tm_vt, t->vt, 1, vt_rows, t->Tp, t->Tp, 64, 64));
+    B200_TRY(make_tmap_3d(&t->tm_qkv3, t->qkv, 1, (uint64_t)m->cfg.max_batch, (uint64_t)T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128));
   }
   return B200_OK;
 }
@@ -193,7 +197,9 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     }
     B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
-      if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
+      if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
+        B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+      else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
         B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
@@ -333,6 +339,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
   m->cfg = *cfg;
   m->device = device;
   m->sms = sm_count(device);
+  if (const char* g = getenv("B200_ATTN_GEN")) m->attn_gen = atoi(g);
   m->grid = cfg->image_size / cfg->patch;
   const int k_raw = 3 * cfg->patch * cfg->patch;
   m->Kp = (k_raw + 63) / 64 * 64;
@@ -558,6 +565,13 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
   B200_TRY(make_tmap_2d(&tq, d_qkv, 1, (uint64_t)B * T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128, 64));
   if (d_vt) B200_TRY(make_tmap_2d(&tv, d_vt, 1, (uint64_t)B * heads * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 64));
   else tv = tq;
+  // Tp == -2: third generation (attention_tc3.cu), per-sample 3-D tensor map
+  if (Tp == -2) {
+    CUtensorMap t3;
+    B200_TRY(make_tmap_3d(&t3, d_qkv, 1, (uint64_t)B, (uint64_t)T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128));
+    return attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
+                         (cudaStream_t)stream);
+  }
   // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu)
   if (Tp < 0)
     return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),

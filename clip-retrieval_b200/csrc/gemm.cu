@@ -45,6 +45,26 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t row
   return B200_OK;
 }
 
+// 3-D tensor [n2, n1, n0] (16-bit elements, innermost n0 contiguous, row pitch ld_elems, sample pitch n1 * ld_elems),
+// boxes of 1 x box_rows x 64 elements with the 128-byte swizzle; rows >= n1 of a box are zero-filled.
+int make_tmap_3d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t n2, uint64_t n1, uint64_t n0, uint64_t ld_elems,
+                 uint32_t box_rows) {
+  encode_tiled_fn enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  B200_CHECK(((uintptr_t)ptr & 15) == 0 && (ld_elems * 2) % 16 == 0, B200_ERR_INVALID,
+             "tensor map: base and row pitch must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld_elems);
+  B200_CHECK(box_rows >= 1 && box_rows <= 256 && n0 >= 64, B200_ERR_INVALID, "tensor map: bad 3-D box");
+  cuuint64_t dims[3] = {n0, n1, n2};
+  cuuint64_t strides[2] = {ld_elems * 2, n1 * ld_elems * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, dtype_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with %d", (int)r);
+  return B200_OK;
+}
+
 static bool g_pair_enabled = true;
 void gemm_set_pair_mode(bool on) { g_pair_enabled = on; }
 

@@ -205,6 +205,13 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
         err3 = (out3.float() - ref).abs()
         assert not torch.isnan(out3.float()).any()
         assert bool((err3 <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc2 max err %g" % err3.max().item()
+        # fourth variant (production): one score pass against a Cauchy-Schwarz bound, leftover rows on the FMA pipe
+        out4 = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+        check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -2, out4.data_ptr(), B, T, heads, w, causal, 0,
+                                                torch.cuda.current_stream().cuda_stream), "attention_tc3")
+        err4 = (out4.float() - ref).abs()
+        assert not torch.isnan(out4.float()).any()
+        assert bool((err4 <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc3 max err %g" % err4.max().item()
 
 
 @pytest.mark.timeout(120)
@@ -223,10 +230,55 @@ def test_tcgen05_attention_second_key_block_dominates():
     kview[1, 200:230, 1, 0] *= 6.0    # sample 1, head 0 only
     qkv = qkv.bfloat16()
     out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
-    check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out.data_ptr(), B, T, heads, w, 0, 0,
-                                            torch.cuda.current_stream().cuda_stream), "attention_tc2")
     q, k, vv = qkv.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, -1) @ vv).transpose(1, 2).reshape(B * T, w)
-    err = (out.float() - ref).abs()
-    assert not torch.isnan(out.float()).any()
-    assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), "max err %g" % err.max().item()
+    for gen in (-1, -2):
+        out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+        check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, gen, out.data_ptr(), B, T, heads, w, 0, 0,
+                                                torch.cuda.current_stream().cuda_stream), "attention_tc%d" % (1 - gen))
+        err = (out.float() - ref).abs()
+        assert not torch.isnan(out.float()).any()
+        assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), "gen %d max err %g" % (gen, err.max().item())
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("T,causal", [(257, 0), (77, 1), (200, 0)])
+def test_tcgen05_attention_single_pass_bound_and_fallback(T, causal):
+    """attention_tc3 subtracts a Cauchy-Schwarz bound |q| * max|k| instead of the row maximum.  (a) Keys with a huge
+    norm that are nearly orthogonal to every query push the bound far above the true maximum: the kernel must detect
+    the slack and repeat the pass with exact maxima.  (b) Large aligned scores (true maximum near the bound, scores
+    spread over > 100 log2 units) must neither overflow nor lose the small terms that still matter.  (c) A sample
+    whose neighbour in the batch holds non-finite activations must not be contaminated (per-sample tensor maps)."""
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    B, heads, hd = 3, 4, 64
+    w = heads * hd
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = torch.randn(B * T, 3 * w, device="cuda", generator=g)
+    view = qkv.view(B, T, 3, heads, hd)
+    # (a) sample 0: key 3 of every head is 400x larger but lives (almost) in one coordinate the queries avoid
+    view[0, :, 0, :, 0] = 0.0
+    view[0, 3, 1] = 0.0
+    view[0, 3, 1, :, 0] = 4000.0
+    # (b) sample 1: queries and a few keys strongly aligned and large
+    view[1, :, 0, 0] *= 6.0
+    view[1, 10:14, 1, 0] = view[1, 20, 0, 0] * 1.5
+    qkv = qkv.bfloat16()
+    ref_in = qkv.clone()
+    # (c) sample 2 is poisoned AFTER the reference is computed for samples 0/1 on clean data
+    poisoned = qkv.clone()
+    poisoned.view(B, T, 3, heads, hd)[2] = float("inf")
+    out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib.b200_attention_tc_bf16_device(poisoned.data_ptr(), None, -2, out.data_ptr(), B, T, heads, w, causal, 0,
+                                            torch.cuda.current_stream().cuda_stream), "attention_tc3")
+    q, k, vv = ref_in.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), device="cuda").triu_(1)
+    ref = (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(B, T, w)
+    got = out.float().view(B, T, w)
+    for b in (0, 1):
+        assert not torch.isnan(got[b]).any() and not torch.isinf(got[b]).any(), "sample %d" % b
+        err = (got[b] - ref[b]).abs()
+        assert bool((err <= ref[b].abs() * 2 ** -6 + 3e-2).all()), "sample %d max err %g" % (b, err.max().item())

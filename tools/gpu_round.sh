@@ -1,0 +1,14 @@
+#!/bin/bash
+# One GPU-box session: new-kernel tests first (under a hard timeout), then the whole -m gpu suite, the bench, and the
+# serving-shape launch list.  Everything lands in gpurun_out/<tag>_*.
+tag=${1:-r02}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_embed_gpu.py -q -k tcgen05 -p no:cacheprovider > gpurun_out/${tag}_attn.log 2>&1
+rc=$?; echo "attention tests rc=$rc" | tee -a gpurun_out/${tag}_attn.log; tail -4 gpurun_out/${tag}_attn.log
+if [ $rc -ne 0 ]; then export B200_ATTN_GEN=2; echo "falling back to attention_tc2 for the rest of this session"; fi
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider --deselect tests/test_embed_gpu.py::test_tcgen05_attention_matches_fp32_reference > gpurun_out/${tag}_pytest.log 2>&1
+echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -6 gpurun_out/${tag}_pytest.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+echo "bench rc=$?"; tail -c 1500 gpurun_out/${tag}_bench.err; head -c 1200 gpurun_out/${tag}_bench.json; echo
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_serve_launches.csv python tools/serve_shapes.py --reps 2 > gpurun_out/${tag}_serve.log 2>&1
+timeout 120 python tools/serve_shapes.py --reps 20 > gpurun_out/${tag}_serve_plain.log 2>&1; cat gpurun_out/${tag}_serve_plain.log
