@@ -22,7 +22,8 @@ namespace b200 {
 
 struct Linear {
   __nv_bfloat16* w = nullptr;  // [N, K]
-  float* b = nullptr;          // [N] or null
+  float* b = nullptr;          // [N] or null (folded LayerNorm: d[n] = sum_k beta[k] W[n,k] + b[n])
+  float* lnc = nullptr;        // folded LayerNorm: c[n] = sum_k W'[n,k], W' = bf16(W * gamma)  (gemm.cuh)
   int N = 0, K = 0;
   CUtensorMap tm256, tm128;
 };
@@ -37,7 +38,8 @@ struct Tower {
   std::vector<Layer> L;
   // activations
   __nv_bfloat16 *x = nullptr, *h = nullptr, *qkv = nullptr, *a = nullptr, *f = nullptr;
-  CUtensorMap tm_h, tm_a, tm_f;
+  CUtensorMap tm_h, tm_a, tm_f, tm_x;
+  float2* stats = nullptr;     // folded LayerNorm: (mean, M2) per 64-column slot of every row of x
   // tcgen05 attention (head dim 64, T <= 320): V^T buffer + maps over qkv / V^T
   bool use_tc_attn = false;
   int Tp = 0;
@@ -82,6 +84,7 @@ struct b200_clip {
   bool act_used = false;
   // timing
   bool profiling = false;
+  bool fuse_ln = true;         // LayerNorm of every block folded into the qkv / fc GEMMs (B200_FUSE_LN=0: separate kernel)
   int attn_gen = 3;            // 3: attention_tc3.cu (single score pass); 2: attention_tc2.cu (B200_ATTN_GEN, A/B runs)
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
   bool attn_v_direct = true;   // P.V reads V from the qkv buffer as an MN-major operand (no V^T copy)
@@ -142,6 +145,14 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
   B200_TRY(make_tmap_2d(&t->tm_h, t->h, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_a, t->a, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_f, t->f, 1, rows, c.mlp, c.mlp, GEMM_BM, GEMM_BK));
+  B200_TRY(make_tmap_2d(&t->tm_x, t->x, 1, rows, w, w, GEMM_BM, GEMM_BK));
+  if (m->fuse_ln && w % 64 == 0) {
+    B200_TRY(dev_alloc(m, &t->stats, rows * (size_t)(w / 64)));
+    for (auto& L : t->L) {
+      B200_TRY(dev_alloc(m, &L.qkv.lnc, (size_t)3 * w));
+      B200_TRY(dev_alloc(m, &L.fc.lnc, (size_t)c.mlp));
+    }
+  }
   t->use_tc_attn = attention_tc_supported(T, c.heads, w);
   if (t->use_tc_attn) {
     t->Tp = (T + 7) / 8 * 8;
@@ -188,14 +199,22 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
   const int w = t.width;
   const int M = B * t.T;
   const int act = m->cfg.quick_gelu ? ACT_QUICK_GELU : ACT_GELU;
+  const bool fused = t.stats != nullptr;   // LayerNorm folded into the qkv / fc GEMMs (weights carry gamma)
+  if (fused) {
+    // records of the stream as it enters the first block (after ln_pre / the embedding lookup); every later
+    // version of x comes out of a residual GEMM whose epilogue writes them
+    SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+    B200_TRY(row_stats(t.x, M, w, t.stats, st));
+  }
   for (auto& L : t.L) {
-    { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+    if (!fused) { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln1_g, L.ln1_b, M, w, st)); }
     GemmEpilogue e1; e1.out = t.qkv; e1.out_ld = 3 * w;
+    if (fused) { e1.ln_stats = t.stats; e1.ln_c = L.qkv.lnc; e1.ln_w = w; }
     if (t.use_tc_attn && !m->attn_v_direct) {
       e1.vt = t.vt; e1.vt_col0 = 2 * w; e1.vt_T = t.T; e1.vt_Tp = t.Tp; e1.vt_hd = 64; e1.vt_heads = t.heads;
     }
-    B200_TRY(run_linear(m, t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
+    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
         B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
@@ -204,12 +223,15 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
+    if (fused) e2.stats_out = t.stats;
     B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st, CLS_G_OUT));
-    { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
+    if (!fused) { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln2_g, L.ln2_b, M, w, st)); }
     GemmEpilogue e3; e3.out = t.f; e3.out_ld = t.mlp; e3.act = act;
-    B200_TRY(run_linear(m, t.tm_h, L.fc, M, e3, st, CLS_G_FC));
+    if (fused) { e3.ln_stats = t.stats; e3.ln_c = L.fc.lnc; e3.ln_w = w; }
+    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.fc, M, e3, st, CLS_G_FC));
     GemmEpilogue e4; e4.out = t.x; e4.out_ld = w; e4.residual = t.x; e4.res_ld = w;
+    if (fused) e4.stats_out = t.stats;
     B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st, CLS_G_PROJ));
   }
   return B200_OK;
@@ -298,13 +320,58 @@ struct Loader {
   }
 };
 
+// Folded LayerNorm (gemm.cuh): W' = bf16(W * gamma) replaces W; c[n] = sum_k W'[n,k] (of the ROUNDED weights — what
+// the tensor core multiplies); d[n] = sum_k beta[k] W[n,k] + b[n] replaces the bias.
+static int put_folded(Loader& ld, const std::string& wname, const std::string& bname, const std::string& gname,
+                      const std::string& betaname, Linear& l) {
+  const size_t N = l.N, K = l.K;
+  const b200_tensor_view* W = ld.find(wname, N * K);
+  const b200_tensor_view* bv = ld.find(bname, N);
+  const b200_tensor_view* g = ld.find(gname, K);
+  const b200_tensor_view* be = ld.find(betaname, K);
+  if (!W || !bv || !g || !be) return B200_ERR_INVALID;
+  std::vector<uint16_t> w16(N * K);
+  std::vector<float> c(N), d(N);
+  for (size_t n = 0; n < N; n++) {
+    double cs = 0.0, ds = 0.0;
+    for (size_t k = 0; k < K; k++) {
+      const float wv = view_get(*W, n * K + k);
+      const uint16_t h = f32_to_bf16_rn(wv * view_get(*g, k));
+      w16[n * K + k] = h;
+      uint32_t u = (uint32_t)h << 16;
+      float hf;
+      memcpy(&hf, &u, 4);
+      cs += (double)hf;
+      ds += (double)view_get(*be, k) * (double)wv;
+    }
+    c[n] = (float)cs;
+    d[n] = (float)(ds + (double)view_get(*bv, n));
+  }
+  B200_CUDA(cudaMemcpy(l.w, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(l.lnc, c.data(), N * 4, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(l.b, d.data(), N * 4, cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
 static int load_tower(Loader& ld, Tower& t, const std::string& prefix) {
   const size_t w = t.width, mlp = t.mlp;
+  const bool fused = t.stats != nullptr;
   for (int i = 0; i < t.layers; i++) {
     Layer& L = t.L[i];
     const std::string p = prefix + "transformer.resblocks." + std::to_string(i) + ".";
     B200_TRY(ld.put_f32(p + "ln_1.weight", L.ln1_g, w));
     B200_TRY(ld.put_f32(p + "ln_1.bias", L.ln1_b, w));
+    if (fused) {
+      B200_TRY(put_folded(ld, p + "attn.in_proj_weight", p + "attn.in_proj_bias", p + "ln_1.weight", p + "ln_1.bias", L.qkv));
+      B200_TRY(put_folded(ld, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "ln_2.weight", p + "ln_2.bias", L.fc));
+      B200_TRY(ld.put_bf16(p + "attn.out_proj.weight", L.out.w, w, w, w));
+      B200_TRY(ld.put_f32(p + "attn.out_proj.bias", L.out.b, w));
+      B200_TRY(ld.put_f32(p + "ln_2.weight", L.ln2_g, w));
+      B200_TRY(ld.put_f32(p + "ln_2.bias", L.ln2_b, w));
+      B200_TRY(ld.put_bf16(p + "mlp.c_proj.weight", L.proj.w, w, mlp, mlp));
+      B200_TRY(ld.put_f32(p + "mlp.c_proj.bias", L.proj.b, w));
+      continue;
+    }
     B200_TRY(ld.put_bf16(p + "attn.in_proj_weight", L.qkv.w, 3 * w, w, w));
     B200_TRY(ld.put_f32(p + "attn.in_proj_bias", L.qkv.b, 3 * w));
     B200_TRY(ld.put_bf16(p + "attn.out_proj.weight", L.out.w, w, w, w));
@@ -340,6 +407,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
   m->device = device;
   m->sms = sm_count(device);
   if (const char* g = getenv("B200_ATTN_GEN")) m->attn_gen = atoi(g);
+  if (const char* g = getenv("B200_FUSE_LN")) m->fuse_ln = atoi(g) != 0;
   m->grid = cfg->image_size / cfg->patch;
   const int k_raw = 3 * cfg->patch * cfg->patch;
   m->Kp = (k_raw + 63) / 64 * 64;

@@ -17,6 +17,8 @@ int text_embed(const int64_t* tokens, const __nv_bfloat16* tok_emb, const float*
 // rows of `w` bf16 elements, in_ld/out_ld in elements; in == out allowed.
 int layernorm_rows(const __nv_bfloat16* in, int64_t in_ld, __nv_bfloat16* out, int64_t out_ld, const float* gamma,
                    const float* beta, int64_t rows, int w, cudaStream_t st);
+// (mean, M2) per 64-column slot of every row of x [rows, w] (w % 64 == 0): seeds GemmEpilogue::ln_stats.
+int row_stats(const __nv_bfloat16* x, int64_t rows, int w, float2* stats, cudaStream_t st);
 // K4: multi-head attention over the fused qkv buffer [B*T, 3w] -> out [B*T, w]; causal for text.
 int attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w, int causal, cudaStream_t st);
 // K4 on tcgen05 (attention_tc.cu): head dim 64, T <= 320.  tmQK: qkv buffer [rows, 3w] box 128x64;

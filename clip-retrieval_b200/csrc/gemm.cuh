@@ -43,6 +43,17 @@ struct GemmEpilogue {
   int64_t out_ld = 0;
   int out_group = 0;                        // > 0: out row = (row / g) * (g + 1) + 1 + row % g  (cls slot)
   int act = ACT_NONE;
+  // LayerNorm folded into this GEMM (K5/K6 of SURVEY §2.2 without a separate normalisation pass): A is the RAW
+  // residual stream x and the weights carry gamma (W'[n,k] = W[n,k] * gamma[k]), so
+  //   LN(x) W^T + b = rstd * (x W'^T - mean * c) + d,   c[n] = sum_k W'[n,k],  d[n] = sum_k beta[k] W[n,k] + b[n].
+  // ln_stats: per row, ln_w / 64 records (mean, M2) of 64-column slots of x, written by the producer's epilogue
+  // (stats_out below); ln_c = c (fp32 [N]); `bias` then points at d.
+  const float2* ln_stats = nullptr;
+  const float* ln_c = nullptr;
+  int ln_w = 0;
+  // Row statistics of what this epilogue stores (bf16-rounded), one (mean, M2) record per 64 output columns:
+  // stats_out[row * (N / 64) + slot].  Set on the GEMMs that write the residual stream.
+  float2* stats_out = nullptr;
   // Optional transposed store of the V third of a QKV projection (columns >= vt_col0): element
   // (row = b*T + t, col = vt_col0 + h*hd + dd) goes to vt[((b*heads + h)*hd + dd) * vt_Tp + t], i.e. V^T
   // per (sample, head) with keys contiguous — the K-major B operand of the P.V MMA (attention_tc.cu).
@@ -59,7 +70,21 @@ struct EpiRow {
   __nv_bfloat16* out_ptr;
   const __nv_bfloat16* res_ptr;
   __nv_bfloat16* vt_ptr;   // vt + (b*heads*hd) * Tp + t   (add (h*hd + dd) * Tp)
+  float ln_a, ln_b;        // folded LayerNorm: value = acc * ln_a + (ln_b * c[col] + d[col]);  (1, 0) when off
 };
+// (mean, rstd) of a row from its 64-column slot records (Chan's combination of equal-sized groups)
+__device__ __forceinline__ void ln_row_coeffs(const float2* __restrict__ rec, int slots, int w, float& a, float& b) {
+  float msum = 0.f, m2 = 0.f;
+  for (int i = 0; i < slots; i++) msum += rec[i].x;
+  const float mean = msum / (float)slots;
+  for (int i = 0; i < slots; i++) {
+    const float dm = rec[i].x - mean;
+    m2 += rec[i].y + 64.0f * dm * dm;
+  }
+  const float rstd = rsqrtf(fmaxf(m2 / (float)w, 0.f) + 1e-5f);
+  a = rstd;
+  b = -mean * rstd;
+}
 __device__ __forceinline__ EpiRow epi_row(const GemmEpilogue& ep, int row, int n0) {
   EpiRow r;
   int64_t out_row = row;
@@ -69,6 +94,8 @@ __device__ __forceinline__ EpiRow epi_row(const GemmEpilogue& ep, int row, int n
   r.out_ptr = ep.out + out_row * ep.out_ld + n0;
   r.res_ptr = ep.residual ? ep.residual + res_row * ep.res_ld + n0 : nullptr;
   r.vt_ptr = nullptr;
+  r.ln_a = 1.0f;
+  r.ln_b = 0.0f;
   if (ep.vt) {
     const int b = row / ep.vt_T, t = row - b * ep.vt_T;
     r.vt_ptr = ep.vt + (int64_t)b * ep.vt_heads * ep.vt_hd * ep.vt_Tp + t;
@@ -82,7 +109,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN * 4 + 256 + 1024;  // ring + bias + barriers + align slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 256 + 1024;  // ring + bias + LN c + barriers + align slack
   static constexpr int TMEM_COLS = 2 * BN;                                         // 512 or 256
 };
 
@@ -120,11 +147,20 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // bias + activation + residual + bf16 store of 8 consecutive columns (col = offset inside the tile)
 // `rr` = the residual's 8 values, prefetched before the accumulator wait (its HBM latency would
 // otherwise sit in the middle of the epilogue: 57% of the stall samples in profiles/r01c).
+// s_bias = bias (or the folded LayerNorm's d), s_c = the folded LayerNorm's c (read only when ep.ln_stats is set).
+// st_k / st_s / st_q: running shifted sums of the stored values for the row statistics (ep.stats_out).
 __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r8,
-                                           const float* s_bias, int col, int n0, const uint4& rr) {
+                                           const float* s_bias, const float* s_c, int col, int n0, const uint4& rr,
+                                           float st_k, float& st_s, float& st_q) {
   float v[8];
+  if (ep.ln_stats != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+    for (int j = 0; j < 8; j++)
+      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), ep.act);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+  }
   if (er.res_ptr) {
     const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z), dd = unpack_bf16x2(rr.w);
     v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
@@ -142,6 +178,44 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow&
   o.z = pack_bf16x2(v[4], v[5]);
   o.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(er.out_ptr + col) = o;
+  if (ep.stats_out != nullptr) {
+    // statistics of the values as stored (bf16), shifted by the slot's first value to keep the sums small
+    const float2 f0 = unpack_bf16x2(o.x), f1 = unpack_bf16x2(o.y), f2 = unpack_bf16x2(o.z), f3 = unpack_bf16x2(o.w);
+    const float e[8] = {f0.x - st_k, f0.y - st_k, f1.x - st_k, f1.y - st_k, f2.x - st_k, f2.y - st_k, f3.x - st_k, f3.y - st_k};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      st_s += e[j];
+      st_q = fmaf(e[j], e[j], st_q);
+    }
+  }
+}
+
+// One 32-column chunk `c` of the tile for this thread's row: the four 8-column groups, and (stats_out) the
+// (mean, M2) record of a completed 64-column slot (chunks 2j, 2j+1).
+__device__ __forceinline__ void epi_chunk(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r, const float* s_bias,
+                                          const float* s_c, int c, int n0, int N, int row, const uint4* res4, float& st_k,
+                                          float& st_s, float& st_q) {
+  if (ep.stats_out != nullptr && (c & 1) == 0) {
+    // shift = what the first column of the slot will store (bf16): recomputed here, cheap
+    st_s = 0.f;
+    st_q = 0.f;
+    float v0;
+    const int col = c * 32;
+    if (ep.ln_stats != nullptr) v0 = act_apply(fmaf(__uint_as_float(r[0]), er.ln_a, fmaf(er.ln_b, s_c[col], s_bias[col])), ep.act);
+    else v0 = act_apply(__uint_as_float(r[0]) + s_bias[col], ep.act);
+    if (er.res_ptr) v0 += unpack_bf16x2(res4[0].x).x;
+    st_k = __bfloat162float(__float2bfloat16_rn(v0));
+  }
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const int col = c * 32 + g * 8;
+    if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, s_c, col, n0, res4[g], st_k, st_s, st_q);
+  }
+  if (ep.stats_out != nullptr && (c & 1) == 1 && n0 + c * 32 < N) {
+    const float mean = st_k + st_s * (1.0f / 64.0f);
+    const float m2 = fmaxf(st_q - st_s * st_s * (1.0f / 64.0f), 0.f);
+    ep.stats_out[(int64_t)row * (N >> 6) + ((n0 + c * 32) >> 6)] = make_float2(mean, m2);
+  }
 }
 
 template <int BN>
@@ -156,7 +230,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * Cfg::A_BYTES;
   float* s_bias = reinterpret_cast<float*>(base + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + BN);
+  float* s_c = s_bias + BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_c + BN);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -253,12 +328,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = n_blk * BN;
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int j = et; j < BN; j += 256) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      for (int j = et; j < BN; j += 256) {
+        s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+        s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < M;
-      const EpiRow er = epi_row(ep, row, n0);
+      EpiRow er = epi_row(ep, row, n0);
+      if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
+      float st_k = 0.f, st_s = 0.f, st_q = 0.f;
       constexpr int CPW = BN / 64;   // 32-column chunks per epilogue warp
       uint4 res[CPW][4];
 #pragma unroll
@@ -286,13 +366,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
         }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const int col = c * 32 + g * 8;
-            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0, res[ci][g]);
-          }
-        }
+        if (row_ok) epi_chunk(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

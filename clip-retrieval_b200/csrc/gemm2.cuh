@@ -23,7 +23,7 @@ constexpr int G2_STAGES = 6;   // 7 stages (224 KB) measured no better: the issu
 constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;   // 16 KB (half of the 256-wide B tile)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_BN * 4 + 256 + 1024;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 2 * G2_BN * 4 + 256 + 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
@@ -34,7 +34,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   uint8_t* sA = base;
   uint8_t* sB = base + G2_STAGES * G2_A_BYTES;
   float* s_bias = reinterpret_cast<float*>(base + G2_STAGES * G2_STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + G2_BN);
+  float* s_c = s_bias + G2_BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_c + G2_BN);
   uint64_t* empty = full + G2_STAGES;
   uint64_t* tfull = empty + G2_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -155,12 +156,17 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       const int n0 = n_blk * G2_BN;
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-      for (int j = et; j < G2_BN; j += 256) s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+      for (int j = et; j < G2_BN; j += 256) {
+        s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
+        s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
       const int row = m_blk * G2_BM + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = row < M;
-      const EpiRow er = epi_row(ep, row, n0);
+      EpiRow er = epi_row(ep, row, n0);
+      if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
+      float st_k = 0.f, st_s = 0.f, st_q = 0.f;
       constexpr int CPW = G2_BN / 64;   // 32-column chunks per epilogue warp
       // residual prefetch: issued before the accumulator wait so its latency overlaps the main loop
       uint4 res[CPW][4];
@@ -199,13 +205,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
           }
         }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const int col = c * 32 + g * 8;
-            if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, col, n0, res[ci][g]);
-          }
-        }
+        if (row_ok) epi_chunk(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -6,6 +6,9 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_embed_gpu.py -q -k tcgen05 -p no:cacheprovider > gpurun_out/${tag}_attn.log 2>&1
 rc=$?; echo "attention tests rc=$rc" | tee -a gpurun_out/${tag}_attn.log; tail -4 gpurun_out/${tag}_attn.log
 if [ $rc -ne 0 ]; then export B200_ATTN_GEN=2; echo "falling back to attention_tc2 for the rest of this session"; fi
+timeout 600 python -m pytest tests/test_embed_gpu.py -q -k "embeddings_match or vit_l14" -p no:cacheprovider > gpurun_out/${tag}_fuse.log 2>&1
+rc=$?; echo "fused-LN embed tests rc=$rc" | tee -a gpurun_out/${tag}_fuse.log; tail -4 gpurun_out/${tag}_fuse.log
+if [ $rc -ne 0 ]; then export B200_FUSE_LN=0; echo "falling back to the separate LayerNorm kernel for the rest of this session"; fi
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider --deselect tests/test_embed_gpu.py::test_tcgen05_attention_matches_fp32_reference > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -6 gpurun_out/${tag}_pytest.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
