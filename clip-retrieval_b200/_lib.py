@@ -80,6 +80,7 @@ PROTOTYPES = {
     "b200_index_reserve": (_i, [_vp, _i64]),
     "b200_index_add_f16": (_i, [_vp, _vp, _i64, _i]),
     "b200_index_add_f32": (_i, [_vp, _vp, _i64, _i]),
+    "b200_index_add_assigned_f16": (_i, [_vp, _vp, _i64, _i, _vp]),
     "b200_index_add_synthetic": (_i, [_vp, _i64, _i64, C.POINTER(SynthSpecC)]),
     "b200_index_finalize": (_i, [_vp]),
     "b200_index_ntotal": (_i64, [_vp]),

@@ -22,6 +22,9 @@ int ivf_lists(b200_index* idx, int64_t* h_sizes, int64_t* h_ids);
 void ivf_free(b200_index* idx);
 int range_scan(b200_index* idx, const __half* rows, int64_t n, const float* d_q, float thresh, unsigned long long* d_out,
                unsigned int cap, unsigned int* d_count, cudaStream_t st);
+int ivf_range_scan(b200_index* idx, const float* d_q, float thresh, unsigned long long* d_out, unsigned int cap,
+                   unsigned int* d_count, cudaStream_t st);
+int ivf_id_to_slot(b200_index* idx, const uint32_t** out);
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,6 +300,19 @@ int b200_index_add_f32(b200_index* idx, const float* rows, int64_t n, int rows_o
   return add_rows(idx, rows, n, rows_on_device, true);
 }
 
+int b200_index_add_assigned_f16(b200_index* idx, const void* rows, int64_t n, int rows_on_device, const int32_t* h_lists) {
+  B200_CHECK(idx && h_lists, B200_ERR_INVALID, "add_assigned: bad argument");
+  B200_CHECK(idx->nlist > 0, B200_ERR_STATE, "add_assigned: not an IVF index");
+  for (int64_t i = 0; i < n; i++)
+    B200_CHECK(h_lists[i] >= 0 && h_lists[i] < idx->nlist, B200_ERR_INVALID, "add_assigned: row %lld has list %d of %d",
+               (long long)i, h_lists[i], idx->nlist);
+  const int64_t before = idx->npending;
+  B200_TRY(add_rows(idx, rows, n, rows_on_device, false));
+  idx->pending_lists.resize((size_t)before, 0xFFFFFFFFu);
+  for (int64_t i = 0; i < n; i++) idx->pending_lists.push_back((uint32_t)h_lists[i]);
+  return B200_OK;
+}
+
 int b200_index_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec) {
   B200_CHECK(idx && spec && n >= 0, B200_ERR_INVALID, "add_synthetic: bad argument");
   if (n == 0) return B200_OK;
@@ -411,7 +427,6 @@ int b200_index_search(b200_index* idx, const float* h_q, int nq, int k, float* h
 int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int64_t cap, float* h_D, int64_t* h_I,
                             int64_t* h_count) {
   B200_CHECK(idx && h_q && h_count && cap >= 0 && (cap == 0 || (h_D && h_I)), B200_ERR_INVALID, "range_search: bad argument");
-  B200_CHECK(idx->nlist == 0, B200_ERR_UNSUPPORTED, "range_search is implemented for the flat index");
   B200_CHECK(cap < (1ll << 31), B200_ERR_INVALID, "range_search: cap too large");
   std::lock_guard<std::mutex> lock(idx->mu);
   DeviceGuard g(idx->device);
@@ -425,14 +440,19 @@ int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int
   int64_t* d_I = (int64_t*)((char*)d_D + (((size_t)cap * 4 + 7) & ~(size_t)7));
   B200_TRY(scratch_acquire(idx, 0));
   B200_CUDA(cudaMemcpyAsync(d_q, h_q, (size_t)idx->d * 4, cudaMemcpyHostToDevice, 0));
-  B200_TRY(range_scan(idx, idx->rows, idx->ntotal, d_q, thresh, d_keys, (unsigned int)cap, d_count, 0));
+  if (idx->nlist > 0) {
+    B200_TRY(ivf_finalize(idx));
+    B200_TRY(ivf_range_scan(idx, d_q, thresh, d_keys, (unsigned int)cap, d_count, 0));
+  } else {
+    B200_TRY(range_scan(idx, idx->rows, idx->ntotal, d_q, thresh, d_keys, (unsigned int)cap, d_count, 0));
+  }
   unsigned int cnt = 0;
   B200_CUDA(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, 0));
   B200_CUDA(cudaStreamSynchronize(0));
   *h_count = cnt;
   const int64_t m = std::min<int64_t>(cnt, cap);
   if (m > 0) {
-    B200_TRY(decode_keys(d_keys, m, idx->id_base, nullptr, d_D, d_I, 0));
+    B200_TRY(decode_keys(d_keys, m, idx->id_base, idx->nlist > 0 ? idx->row_ids : nullptr, d_D, d_I, 0));
     B200_CUDA(cudaMemcpyAsync(h_D, d_D, (size_t)m * 4, cudaMemcpyDeviceToHost, 0));
     B200_CUDA(cudaMemcpyAsync(h_I, d_I, (size_t)m * 8, cudaMemcpyDeviceToHost, 0));
     B200_CUDA(cudaStreamSynchronize(0));
@@ -442,11 +462,16 @@ int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int
 
 int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t n, float* d_R, void* stream) {
   B200_CHECK(idx && d_ids && d_R && n >= 0, B200_ERR_INVALID, "reconstruct: bad argument");
-  B200_CHECK(idx->nlist == 0, B200_ERR_UNSUPPORTED, "reconstruct by id is implemented for the flat index");
   if (n == 0) return B200_OK;
   DeviceGuard g(idx->device);
+  const uint32_t* id_to_slot = nullptr;
+  if (idx->nlist > 0) {
+    std::lock_guard<std::mutex> lock(idx->mu);
+    B200_TRY(ivf_finalize(idx));
+    B200_TRY(ivf_id_to_slot(idx, &id_to_slot));
+  }
   gather_rows_from_slots_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      idx->rows, idx->d, d_ids, idx->id_base, idx->ntotal, nullptr, n, d_R);
+      idx->rows, idx->d, d_ids, idx->id_base, idx->ntotal, id_to_slot, n, d_R);
   B200_LAUNCH_OK();
   return B200_OK;
 }

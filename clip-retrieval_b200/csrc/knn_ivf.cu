@@ -97,6 +97,16 @@ __global__ void lists_by_construction_kernel(uint32_t* __restrict__ lists, uint3
   idx[i] = (uint32_t)i;
 }
 
+__global__ void apply_explicit_lists_kernel(const uint32_t* __restrict__ explicit_lists, int64_t n, uint32_t* __restrict__ lists) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && explicit_lists[i] != 0xFFFFFFFFu) lists[i] = explicit_lists[i];
+}
+
+__global__ void invert_ids_kernel(const uint32_t* __restrict__ row_ids, int64_t n, uint32_t* __restrict__ id_to_slot) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id_to_slot[row_ids[i]] = (uint32_t)i;
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ idx, int64_t n, uint32_t base) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) idx[i] = base + (uint32_t)i;
@@ -275,6 +285,7 @@ void ivf_free(b200_index* idx) {
   if (idx->list_offsets) cudaFree(idx->list_offsets);
   if (idx->row_ids) cudaFree(idx->row_ids);
   if (idx->pending) cudaFree(idx->pending);
+  if (idx->id_to_slot) cudaFree(idx->id_to_slot);
 }
 
 // Sort (list, src) pairs by list (stable) and derive list offsets; `lists`/`src` are device arrays of n.
@@ -327,6 +338,18 @@ int ivf_finalize(b200_index* idx) {
   afn<<<(unsigned)((nnew + 7) / 8), 256>>>(reinterpret_cast<const uint4*>(idx->pending), nnew, cpr,
                                            reinterpret_cast<const uint4*>(idx->centroids), idx->nlist, lists + nold);
   B200_LAUNCH_OK();
+  if (!idx->pending_lists.empty()) {
+    // rows added with an explicit list (an index file's own inverted lists) keep it
+    idx->pending_lists.resize((size_t)nnew, 0xFFFFFFFFu);
+    uint32_t* d_explicit = nullptr;
+    B200_CUDA(cudaMalloc((void**)&d_explicit, (size_t)nnew * 4));
+    B200_CUDA(cudaMemcpy(d_explicit, idx->pending_lists.data(), (size_t)nnew * 4, cudaMemcpyHostToDevice));
+    apply_explicit_lists_kernel<<<(unsigned)((nnew + 255) / 256), 256>>>(d_explicit, nnew, lists + nold);
+    B200_LAUNCH_OK();
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaFree(d_explicit));
+    idx->pending_lists.clear();
+  }
   iota_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, n, 0u);
   B200_LAUNCH_OK();
   uint32_t* sorted_src = nullptr;
@@ -354,6 +377,7 @@ int ivf_finalize(b200_index* idx) {
   idx->row_ids = nids;
   idx->capacity = n;
   idx->ntotal = n;
+  idx->id_to_slot_n = -1;
   return refresh_host_offsets(idx);
 }
 
@@ -472,6 +496,118 @@ int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned l
     B200_TRY(launch_topk_select(k1, M, M, k, C, k2, (int64_t)slices * k, slices, qb, st));
     B200_TRY(launch_topk_select(k2, (int64_t)slices * k, (int64_t)slices * k, k, C, d_keys + (size_t)q0 * k, k, 1, qb, st));
   }
+  return B200_OK;
+}
+
+// id -> slot map for reconstruct-by-id on the list-ordered store (built once per finalize)
+int ivf_id_to_slot(b200_index* idx, const uint32_t** out) {
+  if (idx->id_to_slot_n != idx->ntotal) {
+    if (idx->id_to_slot) B200_CUDA(cudaFree(idx->id_to_slot));
+    idx->id_to_slot = nullptr;
+    if (idx->ntotal > 0) {
+      B200_CUDA(cudaMalloc((void**)&idx->id_to_slot, (size_t)idx->ntotal * 4));
+      invert_ids_kernel<<<(unsigned)((idx->ntotal + 255) / 256), 256>>>(idx->row_ids, idx->ntotal, idx->id_to_slot);
+      B200_LAUNCH_OK();
+      B200_CUDA(cudaDeviceSynchronize());
+    }
+    idx->id_to_slot_n = idx->ntotal;
+  }
+  *out = idx->id_to_slot;
+  return B200_OK;
+}
+
+// ---- range search over the probed lists (index.range_search on an IVF index: clip_filter.py:52) -----------
+// FAISS IndexIVF::range_search visits the nprobe lists of the query and reports every row whose inner product
+// exceeds the threshold.  One CTA per (probe, segment); hits are appended as (score, slot) keys.
+template <int CH>
+__global__ void __launch_bounds__(256)
+ivf_range_kernel(const uint4* __restrict__ X, int cpr, const float* __restrict__ Q, const unsigned long long* __restrict__ probes,
+                 int nprobe, int segs, const int64_t* __restrict__ offsets, float thresh, unsigned long long* __restrict__ out,
+                 unsigned int cap, unsigned int* __restrict__ counter) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int seg = blockIdx.x % segs;
+  const int p = blockIdx.x / segs;
+  const unsigned long long pk = probes[p];
+  if (pk == 0ull) return;
+  const uint32_t l = key_id(pk);
+  const int64_t lbeg = offsets[l], lend = offsets[l + 1];
+  const int64_t per = (((lend - lbeg) + segs - 1) / segs + SCAN_ALIGN - 1) / SCAN_ALIGN * SCAN_ALIGN;
+  const int64_t beg = lbeg + (int64_t)seg * per;
+  const int64_t end = beg + per < lend ? beg + per : lend;
+  float qr[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    const int ci = c * 32 + lane;
+    if (ci < cpr) {
+      const float4 a = *reinterpret_cast<const float4*>(Q + ci * 8);
+      const float4 b = *reinterpret_cast<const float4*>(Q + ci * 8 + 4);
+      qr[c][0] = a.x; qr[c][1] = a.y; qr[c][2] = a.z; qr[c][3] = a.w;
+      qr[c][4] = b.x; qr[c][5] = b.y; qr[c][6] = b.z; qr[c][7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) qr[c][j] = 0.f;
+    }
+  }
+  for (int64_t r0 = beg + (int64_t)warp * 4; r0 < end; r0 += (int64_t)nwarps * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const int ci = c * 32 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + u < end && ci < cpr) v = ld_nc_v4(X + (r0 + u) * cpr + ci);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 t = __half22float2(h2[j]);
+          acc[u] = fmaf(t.x, qr[c][2 * j], acc[u]);
+          acc[u] = fmaf(t.y, qr[c][2 * j + 1], acc[u]);
+        }
+      }
+    }
+    warp_transpose_reduce<4>(acc, lane);
+    const int64_t my_r = r0 + (lane >> 3);
+    if ((lane & 7) == 0 && my_r < end && acc[0] > thresh) {
+      const unsigned int pos = atomicAdd(counter, 1u);
+      if (pos < cap) out[pos] = make_key(acc[0], (uint32_t)my_r);
+    }
+  }
+}
+
+typedef void (*ivf_range_fn)(const uint4*, int, const float*, const unsigned long long*, int, int, const int64_t*, float,
+                             unsigned long long*, unsigned int, unsigned int*);
+static ivf_range_fn pick_ivf_range(int ch) {
+  switch (ch) {
+    case 1: return ivf_range_kernel<1>;
+    case 2: return ivf_range_kernel<2>;
+    case 3: return ivf_range_kernel<3>;
+    case 4: return ivf_range_kernel<4>;
+    case 5: return ivf_range_kernel<5>;
+    case 6: return ivf_range_kernel<6>;
+    case 7: return ivf_range_kernel<7>;
+    case 8: return ivf_range_kernel<8>;
+  }
+  return nullptr;
+}
+
+// One query (device pointer): (score, slot) keys of every probed row above `thresh`; *d_count = number of hits.
+int ivf_range_scan(b200_index* idx, const float* d_q, float thresh, unsigned long long* d_out, unsigned int cap,
+                   unsigned int* d_count, cudaStream_t st) {
+  const int d = idx->d, cpr = d / 8, ch = (cpr + 31) / 32;
+  const int nprobe = std::min(idx->nprobe, idx->nlist);
+  void* ws = nullptr;
+  B200_TRY(index_ws(idx, 3, (size_t)nprobe * 8, &ws));
+  unsigned long long* probes = (unsigned long long*)ws;
+  B200_TRY(scan_topk_keys(idx, idx->centroids, idx->nlist, d_q, 1, nprobe, probes, st));
+  ivf_range_fn fn = pick_ivf_range(ch);
+  B200_CHECK(fn != nullptr, B200_ERR_UNSUPPORTED, "ivf range_search: unsupported dimension %d", d);
+  B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), st));
+  int segs = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * idx->sms + nprobe - 1) / nprobe));
+  segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, (idx->max_list + 255) / 256));
+  fn<<<(unsigned)(nprobe * segs), 256, 0, st>>>(reinterpret_cast<const uint4*>(idx->rows), cpr, d_q, probes, nprobe, segs,
+                                                 idx->list_offsets, thresh, d_out, cap, d_count);
+  B200_LAUNCH_OK();
   return B200_OK;
 }
 

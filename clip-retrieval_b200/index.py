@@ -192,34 +192,10 @@ class _IndexBase:
         )
         return (D, I, R) if reconstruct else (D, I)
 
-    def set_tensor_scan(self, on):
-        """Batched queries use the tcgen05 scan by default; False forces the FMA scan.  An int is passed
-        through as the C ABI's bit flags (1 tcgen05 scan, 4 no bulk-copy ring, 8 split mode only)."""
-        flags = (1 if on else 0) if isinstance(on, bool) else int(on)
-        check(lib.b200_index_set_tensor_scan(self._h, flags), "set_tensor_scan")
-
-    def last_hi_only_fallbacks(self):
-        return int(lib.b200_index_last_hi_only_fallbacks(self._h))
-
-    def last_scan_ms(self):
-        ms = C.c_float(0)
-        n = C.c_int(0)
-        check(lib.b200_index_last_scan_ms(self._h, C.byref(ms), C.byref(n)), "last_scan_ms")
-        return float(ms.value), int(n.value)
-
-
-class B200FlatIndex(_IndexBase):
-    """Exhaustive inner-product index over fp16 rows (FAISS IndexFlatIP / "SQfp16" semantics)."""
-
-    def __init__(self, d, device=0):
-        super().__init__()
-        self._id_base = 0
-        self.device = device
-        check(lib.b200_index_create_flat(int(d), int(device), C.byref(self._h)), "create_flat")
-
     def range_search(self, x, thresh):
         """index.range_search(x, thresh) -> (lims, D, I): every row with inner product > thresh, per
-        query (clip_filter.py:52; the dedup of clip_back.py:294).  Within a query results are sorted by id."""
+        query (clip_filter.py:52; the dedup of clip_back.py:294) — of the whole flat index, or of the `nprobe`
+        probed lists of an IVF index.  Within a query results are sorted by id."""
         x = _as_query(x, self.d)
         lims = [0]
         Ds, Is = [], []
@@ -249,6 +225,31 @@ class B200FlatIndex(_IndexBase):
         st = torch.cuda.current_stream(ids.device).cuda_stream
         check(lib.b200_index_reconstruct_device(self._h, ids.data_ptr(), 1, out.data_ptr(), st), "reconstruct")
         return out[0].cpu().numpy()
+
+    def set_tensor_scan(self, on):
+        """Batched queries use the tcgen05 scan by default; False forces the FMA scan.  An int is passed
+        through as the C ABI's bit flags (1 tcgen05 scan, 4 no bulk-copy ring, 8 split mode only)."""
+        flags = (1 if on else 0) if isinstance(on, bool) else int(on)
+        check(lib.b200_index_set_tensor_scan(self._h, flags), "set_tensor_scan")
+
+    def last_hi_only_fallbacks(self):
+        return int(lib.b200_index_last_hi_only_fallbacks(self._h))
+
+    def last_scan_ms(self):
+        ms = C.c_float(0)
+        n = C.c_int(0)
+        check(lib.b200_index_last_scan_ms(self._h, C.byref(ms), C.byref(n)), "last_scan_ms")
+        return float(ms.value), int(n.value)
+
+
+class B200FlatIndex(_IndexBase):
+    """Exhaustive inner-product index over fp16 rows (FAISS IndexFlatIP / "SQfp16" semantics)."""
+
+    def __init__(self, d, device=0):
+        super().__init__()
+        self._id_base = 0
+        self.device = device
+        check(lib.b200_index_create_flat(int(d), int(device), C.byref(self._h)), "create_flat")
 
 
 class B200IVFFlatIndex(_IndexBase):
@@ -281,6 +282,14 @@ class B200IVFFlatIndex(_IndexBase):
     def finalize(self):
         check(lib.b200_index_finalize(self._h), "finalize")
 
+    def add_with_lists(self, x, lists):
+        """Append fp16 rows keeping an EXPLICIT inverted list per row (what an existing FAISS IVF file holds)."""
+        x = np.ascontiguousarray(x, dtype=np.float16)
+        lists = np.ascontiguousarray(lists, dtype=np.int32)
+        if x.ndim != 2 or x.shape[1] != self.d or lists.shape != (x.shape[0],):
+            raise ValueError("add_with_lists: expected rows [n, %d] and lists [n]" % self.d)
+        check(lib.b200_index_add_assigned_f16(self._h, x.ctypes.data, x.shape[0], 0, lists.ctypes.data), "add_assigned")
+
     def invlists(self):
         """(sizes [nlist], ids concatenated list after list) — what
         ivf_metadata_ordering.get_old_to_new_mapping reads from FAISS invlists (:46-64)."""
@@ -309,8 +318,18 @@ def load_index(path, enable_faiss_memory_mapping=False, device=0):
     produces (`img_emb/img_emb_{i}.npy`, fp16 row-major; writer.py:67-87).  Shards are appended in
     sorted file order, which is the global row id order.  The rows go
     straight to HBM; `enable_faiss_memory_mapping` is accepted for signature parity and ignored.
+    A FAISS index file (what the reference passes: `image.index`, or a folder holding `populated.index`) is read by
+    faiss_io.read_faiss_index when it is a flat / fp16 / IVF-Flat inner-product index (the types that store rows);
+    quantised-code indices raise NotImplementedError with the way out.
     """
     del enable_faiss_memory_mapping
+    from . import faiss_io
+
+    target = path
+    if os.path.isdir(path) and os.path.exists(os.path.join(path, "populated.index")):
+        target = os.path.join(path, "populated.index")          # clip_back.py:591-592
+    if os.path.isfile(target) and not target.endswith(".npy") and faiss_io.looks_like_faiss_index(target):
+        return index_from_faiss(faiss_io.read_faiss_index(target), device=device)
     files = list_embedding_shards(path)
     first = np.load(files[0], mmap_mode="r")
     index = B200FlatIndex(first.shape[1], device=device)
@@ -379,3 +398,52 @@ def merge_packed_results(gathered, G, stride_bytes, nq, k):
     check(lib.b200_topk_merge_packed_device(gathered.data_ptr(), int(G), C.c_size_t(int(stride_bytes)), int(nq), int(k),
                                             D.data_ptr(), I.data_ptr(), gathered.device.index or 0, st), "topk_merge_packed")
     return D, I
+
+
+class _IdMapped:
+    """Index whose FAISS ids are not 0..n-1 (IndexIDMap, add_with_ids inside IVF lists): results are mapped on the host."""
+
+    def __init__(self, index, id_map):
+        self._index, self._map = index, np.asarray(id_map, dtype=np.int64)
+
+    def __getattr__(self, name):
+        return getattr(self._index, name)
+
+    def _m(self, I):
+        out = np.full_like(I, -1)
+        ok = I >= 0
+        out[ok] = self._map[I[ok]]
+        return out
+
+    def search(self, x, k):
+        D, I = self._index.search(x, k)
+        return D, self._m(I)
+
+    def search_and_reconstruct(self, x, k):
+        D, I, R = self._index.search_and_reconstruct(x, k)
+        return D, self._m(I), R
+
+    def range_search(self, x, thresh):
+        lims, D, I = self._index.range_search(x, thresh)
+        return lims, D, self._m(I)
+
+
+def index_from_faiss(info, device=0):
+    """B200 index from the arrays faiss_io.read_faiss_index returns."""
+    d, ids = info["d"], info["ids"]
+    if info["kind"] == "flat":
+        index = B200FlatIndex(d, device=device)
+        index.reserve(info["ntotal"])
+        rows = info["rows"]
+        step = 1 << 20
+        for s in range(0, rows.shape[0], step):
+            index.add(np.ascontiguousarray(rows[s:s + step]))
+    else:
+        index = B200IVFFlatIndex(d, info["nlist"], info["centroids"], device=device)
+        lists = np.repeat(np.arange(info["nlist"], dtype=np.int32), info["list_sizes"])
+        index.add_with_lists(np.asarray(info["rows"], dtype=np.float16), lists)
+        index.nprobe = max(1, info["nprobe"])
+        index.finalize()
+    if ids is not None and not np.array_equal(ids, np.arange(len(ids), dtype=np.int64)):
+        return _IdMapped(index, ids)
+    return index

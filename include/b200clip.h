@@ -84,6 +84,10 @@ int b200_index_reserve(b200_index* idx, int64_t n);
 /* Append n rows ([n, d] row-major).  Ids are insertion positions + id_base (see set_id_base). */
 int b200_index_add_f16(b200_index* idx, const void* rows, int64_t n, int rows_on_device);
 int b200_index_add_f32(b200_index* idx, const float* rows, int64_t n, int rows_on_device);
+/* IVF only: append n fp16 rows with an EXPLICIT inverted list per row (h_lists[i] in [0, nlist)) instead of the
+ * max-inner-product assignment — how an existing FAISS IVF index file's own lists are kept (load_index,
+ * clip_back.py:589-596). */
+int b200_index_add_assigned_f16(b200_index* idx, const void* rows, int64_t n, int rows_on_device, const int32_t* h_lists);
 /* Append n synthetic rows (rows row0.. of `spec`) generated directly in the row store. */
 int b200_index_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec);
 /* IVF only: rows appended since the last call are bucketed into their inverted lists.  Called
@@ -120,13 +124,15 @@ int b200_index_search(b200_index* idx, const float* h_q, int nq, int k,
  * queries (hi-only tensor scan) synchronises `stream` once to read how many exactness proofs failed. */
 int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k,
                              float* d_D, int64_t* d_I, float* d_R, void* stream);
-/* index.range_search(x, thresh) for ONE query (flat index; reference call sites clip_filter.py:52 and
- * clip_back.py:294): every row whose inner product with h_q exceeds `thresh`.  At most `cap` results
+/* index.range_search(x, thresh) for ONE query (reference call sites clip_filter.py:52 and clip_back.py:294): every
+ * row whose inner product with h_q exceeds `thresh` — of the whole flat index, or of the `nprobe` probed lists of
+ * an IVF index (FAISS IndexIVF::range_search).  At most `cap` results
  * are written (h_D/h_I, unordered); *h_count receives the true number of hits, so a caller that sees
  * *h_count > cap retries with a larger buffer. */
 int b200_index_range_search(b200_index* idx, const float* h_q, float thresh, int64_t cap, float* h_D, int64_t* h_I,
                             int64_t* h_count);
-/* reconstruct(id) for a batch of ids (device buffers): d_R [n, d] fp32; id -1 -> NaN row. */
+/* reconstruct(id) for a batch of ids (device buffers): d_R [n, d] fp32; id -1 -> NaN row.  Flat and IVF (the IVF
+ * store is in list order; an id -> slot map is built on first use). */
 int b200_index_reconstruct_device(b200_index* idx, const int64_t* d_ids, int64_t n, float* d_R, void* stream);
 /* Merge G sorted candidate lists per query into one top-k (the step after the all-gather of
  * per-shard candidates): d_Dg/d_Ig are [G, nq, k]; outputs [nq, k]. */
