@@ -50,6 +50,8 @@ struct Tower {
   __nv_bfloat16* proj = nullptr;             // [width, D]
 };
 
+constexpr int GRAPH_MAX_B = 8;   // forwards of at most this many samples are replayed from a captured graph
+
 enum { CLS_GEMM = 0, CLS_ATTN = 1, CLS_LN = 2, CLS_OTHER = 3,
        CLS_G_QKV = 4, CLS_G_OUT = 5, CLS_G_FC = 6, CLS_G_PROJ = 7, CLS_COUNT = 8 };  // 4..7: per-kind share of CLS_GEMM
 
@@ -84,6 +86,15 @@ struct b200_clip {
   bool act_used = false;
   // timing
   bool profiling = false;
+  // Serving shapes (batch <= GRAPH_MAX_B, clip_back.py:226-246 issues batch 1): the whole tower is captured once into a
+  // CUDA graph per (modality, batch, output type) and replayed — ~75-150 kernel launches become one submission.
+  // The graph works on fixed device buffers (g_in / g_out); a call copies its input in and its result out.
+  struct TowerGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int kernels = 0; };
+  std::map<int, TowerGraph> graphs;   // key: image | B << 1 | f16 << 12 | normalize << 13
+  void* g_in = nullptr;
+  void* g_out = nullptr;
+  bool use_graphs = true;      // B200_GRAPHS=0 disables (A/B, debugging)
+  cudaStream_t cap_stream = nullptr;
   bool fuse_ln = true;         // LayerNorm of every block folded into the qkv / fc GEMMs (B200_FUSE_LN=0: separate kernel)
   int attn_gen = 3;            // 3: attention_tc3.cu (single score pass); 2: attention_tc2.cu (B200_ATTN_GEN, A/B runs)
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
@@ -408,6 +419,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
   m->sms = sm_count(device);
   if (const char* g = getenv("B200_ATTN_GEN")) m->attn_gen = atoi(g);
   if (const char* g = getenv("B200_FUSE_LN")) m->fuse_ln = atoi(g) != 0;
+  if (const char* g = getenv("B200_GRAPHS")) m->use_graphs = atoi(g) != 0;
   m->grid = cfg->image_size / cfg->patch;
   const int k_raw = 3 * cfg->patch * cfg->patch;
   m->Kp = (k_raw + 63) / 64 * 64;
@@ -434,6 +446,11 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
     m->allocs.push_back(m->stage_in);
     B200_CUDA(cudaMalloc(&m->stage_out, (size_t)cfg->max_batch * cfg->embed_dim * 4));
     m->allocs.push_back(m->stage_out);
+    const int gb = std::min(GRAPH_MAX_B, cfg->max_batch);
+    B200_CUDA(cudaMalloc(&m->g_in, std::max((size_t)gb * 3 * cfg->image_size * cfg->image_size * 4, (size_t)gb * cfg->context_length * 8)));
+    m->allocs.push_back(m->g_in);
+    B200_CUDA(cudaMalloc(&m->g_out, (size_t)gb * cfg->embed_dim * 4));
+    m->allocs.push_back(m->g_out);
     return B200_OK;
   };
   rc = build();
@@ -452,6 +469,8 @@ int b200_clip_destroy(b200_clip* m) {
   for (void* p : m->allocs) cudaFree(p);
   for (auto& s : m->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   if (m->act_ev) cudaEventDestroy(m->act_ev);
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   if (m->s_copy) {
     cudaStreamDestroy(m->s_copy); cudaStreamDestroy(m->s_comp);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_done[i]); }
@@ -510,6 +529,46 @@ static int encode_device(b200_clip* m, const void* d_in, int B, void* d_out, int
   const int mb = m->cfg.max_batch;
   const size_t in_stride = image ? (size_t)3 * m->cfg.image_size * m->cfg.image_size * 4 : (size_t)m->cfg.context_length * 8;
   const size_t out_stride = (size_t)m->cfg.embed_dim * (out_dtype == B200_OUT_F16 ? 2 : 4);
+  if (B >= 1 && B <= GRAPH_MAX_B && B <= mb && m->use_graphs && !m->profiling) {
+    // serving shape: replay the captured tower.  First call of a shape runs eagerly (sets kernel attributes,
+    // touches every buffer), the second captures, later ones replay.
+    const int key = (image ? 1 : 0) | (B << 1) | ((out_dtype == B200_OUT_F16 ? 1 : 0) << 12) | ((normalize ? 1 : 0) << 13);
+    b200_clip::TowerGraph& tg = m->graphs[key];
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    B200_CUDA(cudaStreamIsCapturing(st, &cs));
+    if (cs == cudaStreamCaptureStatusNone && tg.seen >= 1) {
+      if (tg.exec == nullptr) {
+        cudaGraph_t graph = nullptr;
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot capture)
+        if (!m->cap_stream) B200_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t cst = m->cap_stream;
+        B200_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
+        int rc = image ? encode_image_chunk(m, (const float*)m->g_in, B, m->g_out, out_dtype == B200_OUT_F16, normalize, cst)
+                       : encode_text_chunk(m, (const int64_t*)m->g_in, B, m->g_out, out_dtype == B200_OUT_F16, normalize, cst);
+        const cudaError_t ce = cudaStreamEndCapture(cst, &graph);
+        if (rc != B200_OK || ce != cudaSuccess || graph == nullptr) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          m->use_graphs = false;   // fall back to eager launches for the life of the handle
+          B200_CHECK(rc == B200_OK, rc, "encode: kernel launch failed during graph capture");
+        } else {
+          const cudaError_t ie = cudaGraphInstantiate(&tg.exec, graph, 0);
+          cudaGraphDestroy(graph);
+          tg.kernels = m->last_launches;   // kernels inside the graph (they were counted once, at capture)
+          if (ie != cudaSuccess) { cudaGetLastError(); tg.exec = nullptr; m->use_graphs = false; }
+        }
+      }
+      if (tg.exec != nullptr) {
+        B200_CUDA(cudaMemcpyAsync(m->g_in, d_in, (size_t)B * in_stride, cudaMemcpyDeviceToDevice, st));
+        B200_CUDA(cudaGraphLaunch(tg.exec, st));
+        B200_CUDA(cudaMemcpyAsync(d_out, m->g_out, (size_t)B * out_stride, cudaMemcpyDeviceToDevice, st));
+        count_launch(tg.kernels);
+        m->last_launches = tg.kernels;
+        return B200_OK;
+      }
+    }
+    tg.seen++;
+  }
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int nb = std::min(mb, B - b0);
     const char* in = (const char*)d_in + (size_t)b0 * in_stride;

@@ -1,6 +1,7 @@
 // The index handle behind b200_index* (flat and IVF-Flat share the row store and the top-k tail).
 #pragma once
 #include "common.cuh"
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -45,6 +46,18 @@ struct b200_index {
   cudaStream_t scratch_stream = nullptr;   // stream waits on it before it reuses ws[] / norm_bound[]
   bool scratch_used = false;
 
+  // Serving shape (nq <= 4: clip_back.py:362 issues one query): the launches of a search are captured once per
+  // (nq, k, nprobe, reconstruct) into a CUDA graph over fixed buffers and replayed; any mutation of the index bumps
+  // graph_epoch and the stale graphs are rebuilt.
+  struct SearchGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int kernels = 0; uint64_t epoch = 0; };
+  std::map<uint64_t, SearchGraph> graphs;
+  uint64_t graph_epoch = 1;
+  bool use_graphs = true;     // B200_GRAPHS=0 disables
+  cudaStream_t cap_stream = nullptr;
+  bool capturing = false;     // timing events are recorded as external event nodes while a graph is captured
+  float* g_q = nullptr; float* g_D = nullptr; int64_t* g_I = nullptr; float* g_R = nullptr;
+  size_t g_q_cap = 0, g_k_cap = 0, g_r_cap = 0;
+
   // scan timing (CUDA events on the launching stream)
   std::vector<cudaEvent_t> ev;   // pairs
   int ev_used = 0;
@@ -52,6 +65,9 @@ struct b200_index {
 };
 
 namespace b200 {
+inline cudaError_t index_record(b200_index* idx, cudaEvent_t e, cudaStream_t st) {
+  return idx->capturing ? cudaEventRecordWithFlags(e, st, cudaEventRecordExternal) : cudaEventRecord(e, st);
+}
 int index_ws(b200_index* idx, int slot, size_t bytes, void** out);
 // Row scan + top-k of nq queries against rows [0, n) of `rows` (row-major fp16, d columns).
 // Writes, per query, k sorted keys (local row ids) into d_keys_out [nq, k].

@@ -5,6 +5,7 @@
 #include "topk.cuh"
 #include <float.h>
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 namespace b200 {
@@ -200,6 +201,7 @@ int b200_index_create_flat(int d, int device, b200_index** out) {
   B200_CHECK(device >= 0 && device < ndev, B200_ERR_INVALID, "create_flat: device %d of %d", device, ndev);
   b200_index* idx = new (std::nothrow) b200_index();
   B200_CHECK(idx != nullptr, B200_ERR_OOM, "create_flat: host allocation failed");
+  if (const char* e = getenv("B200_GRAPHS")) idx->use_graphs = atoi(e) != 0;
   idx->d = d;
   idx->device = device;
   idx->sms = sm_count(device);
@@ -230,6 +232,12 @@ int b200_index_destroy(b200_index* idx) {
     if (b) cudaFree(b);
   for (auto e : idx->ev) cudaEventDestroy(e);
   if (idx->scratch_ev) cudaEventDestroy(idx->scratch_ev);
+  for (auto& kv : idx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (idx->cap_stream) cudaStreamDestroy(idx->cap_stream);
+  if (idx->g_q) cudaFree(idx->g_q);
+  if (idx->g_D) cudaFree(idx->g_D);
+  if (idx->g_I) cudaFree(idx->g_I);
+  if (idx->g_R) cudaFree(idx->g_R);
   ivf_free(idx);
   delete idx;
   return B200_OK;
@@ -239,6 +247,7 @@ int b200_index_reserve(b200_index* idx, int64_t n) {
   B200_CHECK(idx && n >= 0, B200_ERR_INVALID, "reserve: bad argument");
   DeviceGuard g(idx->device);
   idx->reserved = true;
+  idx->graph_epoch++;
   if (idx->nlist > 0) return B200_OK;  // IVF sizes its store at finalize
   return ensure_capacity(idx, n);
 }
@@ -246,6 +255,7 @@ int b200_index_reserve(b200_index* idx, int64_t n) {
 static int add_rows(b200_index* idx, const void* rows, int64_t n, int on_device, bool f32) {
   B200_CHECK(idx && (rows || n == 0) && n >= 0, B200_ERR_INVALID, "add: bad argument");
   if (n == 0) return B200_OK;
+  idx->graph_epoch++;
   DeviceGuard g(idx->device);
   const int d = idx->d;
   __half* dst;
@@ -316,6 +326,7 @@ int b200_index_add_assigned_f16(b200_index* idx, const void* rows, int64_t n, in
 int b200_index_add_synthetic(b200_index* idx, int64_t n, int64_t row0, const b200_synth_spec* spec) {
   B200_CHECK(idx && spec && n >= 0, B200_ERR_INVALID, "add_synthetic: bad argument");
   if (n == 0) return B200_OK;
+  idx->graph_epoch++;
   DeviceGuard g(idx->device);
   if (idx->nlist > 0) return ivf_add_synthetic(idx, n, row0, spec);
   B200_CHECK(idx->ntotal + n < (1ll << 32), B200_ERR_UNSUPPORTED, "add: a shard holds at most 2^32 rows");
@@ -339,6 +350,7 @@ int b200_index_nlist(const b200_index* idx) { return idx ? idx->nlist : -1; }
 
 int b200_index_set_id_base(b200_index* idx, int64_t id_base) {
   B200_CHECK(idx, B200_ERR_INVALID, "set_id_base: null index");
+  idx->graph_epoch++;
   idx->id_base = id_base;
   return B200_OK;
 }
@@ -354,6 +366,7 @@ int b200_index_get_nprobe(const b200_index* idx) { return idx ? idx->nprobe : -1
 
 int b200_index_set_tensor_scan(b200_index* idx, int on) {
   B200_CHECK(idx, B200_ERR_INVALID, "set_tensor_scan: null index");
+  idx->graph_epoch++;
   idx->use_mma = (on & 1) != 0;
   idx->use_staged = (on & 4) == 0;  // bit 2 set: also disable the cp.async.bulk ring (A/B)
   idx->use_hi_only = (on & 8) == 0; // bit 3 set: always the hi/lo split mode (no approximate pass)
@@ -385,13 +398,90 @@ static int scratch_release(b200_index* idx, cudaStream_t st) {
   return B200_OK;
 }
 
+// nq <= 4 through a replayed CUDA graph: returns 1 when the search was served from a graph, 0 when the caller must
+// launch eagerly (first sighting of the shape, graphs disabled, stream already capturing), < 0 on error.
+static int search_graph(b200_index* idx, const float* d_q, int nq, int k, float* d_D, int64_t* d_I, float* d_R,
+                        cudaStream_t st) {
+  constexpr int GRAPH_MAX_NQ = 4;
+  const size_t r_bytes = d_R ? (size_t)nq * k * idx->d * 4 : 0;
+  if (!idx->use_graphs || nq < 1 || nq > GRAPH_MAX_NQ || k > 2048 || r_bytes > (8u << 20) || idx->npending > 0) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  B200_CUDA(cudaStreamIsCapturing(st, &cs));
+  if (cs != cudaStreamCaptureStatusNone) return 0;
+  const uint64_t key = (uint64_t)nq | ((uint64_t)k << 8) | ((uint64_t)(idx->nlist > 0 ? idx->nprobe : 0) << 24) | ((uint64_t)(d_R != nullptr) << 56);
+  b200_index::SearchGraph& sg = idx->graphs[key];
+  if (sg.epoch != idx->graph_epoch) {
+    if (sg.exec) cudaGraphExecDestroy(sg.exec);
+    sg = b200_index::SearchGraph();
+    sg.epoch = idx->graph_epoch;
+  }
+  if (sg.seen < 1) { sg.seen++; return 0; }        // first call of a shape runs eagerly (workspaces, attributes, events)
+  // fixed buffers
+  const size_t qb = (size_t)GRAPH_MAX_NQ * idx->d * 4;
+  if (idx->g_q_cap < qb) {
+    if (idx->g_q) B200_CUDA(cudaFree(idx->g_q));
+    B200_CUDA(cudaMalloc((void**)&idx->g_q, qb));
+    idx->g_q_cap = qb;
+    idx->graph_epoch++; sg.epoch = idx->graph_epoch; if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+  }
+  if (idx->g_k_cap < (size_t)GRAPH_MAX_NQ * k) {
+    if (idx->g_D) B200_CUDA(cudaFree(idx->g_D));
+    if (idx->g_I) B200_CUDA(cudaFree(idx->g_I));
+    B200_CUDA(cudaMalloc((void**)&idx->g_D, (size_t)GRAPH_MAX_NQ * k * 4));
+    B200_CUDA(cudaMalloc((void**)&idx->g_I, (size_t)GRAPH_MAX_NQ * k * 8));
+    idx->g_k_cap = (size_t)GRAPH_MAX_NQ * k;
+    idx->graph_epoch++; sg.epoch = idx->graph_epoch; if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+  }
+  if (r_bytes > idx->g_r_cap) {
+    if (idx->g_R) B200_CUDA(cudaFree(idx->g_R));
+    B200_CUDA(cudaMalloc((void**)&idx->g_R, r_bytes));
+    idx->g_r_cap = r_bytes;
+    idx->graph_epoch++; sg.epoch = idx->graph_epoch; if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+  }
+  if (sg.exec == nullptr) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = g_launches.load();
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); the
+    // instantiated graph is launched on the caller's stream
+    if (!idx->cap_stream) B200_CUDA(cudaStreamCreateWithFlags(&idx->cap_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamBeginCapture(idx->cap_stream, cudaStreamCaptureModeThreadLocal));
+    idx->capturing = true;
+    const int rc = search_device_impl(idx, idx->g_q, nq, k, idx->g_D, idx->g_I, d_R ? idx->g_R : nullptr, idx->cap_stream);
+    idx->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(idx->cap_stream, &graph);
+    if (rc != B200_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      idx->use_graphs = false;
+      return rc != B200_OK ? rc : 0;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); sg.exec = nullptr; idx->use_graphs = false; return 0; }
+    sg.kernels = (int)(g_launches.load() - l0);
+  }
+  B200_CUDA(cudaMemcpyAsync(idx->g_q, d_q, (size_t)nq * idx->d * 4, cudaMemcpyDeviceToDevice, st));
+  B200_CUDA(cudaGraphLaunch(sg.exec, st));
+  B200_CUDA(cudaMemcpyAsync(d_D, idx->g_D, (size_t)nq * k * 4, cudaMemcpyDeviceToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(d_I, idx->g_I, (size_t)nq * k * 8, cudaMemcpyDeviceToDevice, st));
+  if (d_R) B200_CUDA(cudaMemcpyAsync(d_R, idx->g_R, r_bytes, cudaMemcpyDeviceToDevice, st));
+  count_launch(sg.kernels);
+  return 1;
+}
+
 int b200_index_search_device(b200_index* idx, const float* d_q, int nq, int k, float* d_D, int64_t* d_I, float* d_R,
                              void* stream) {
   B200_CHECK(idx, B200_ERR_INVALID, "search: null index");
   std::lock_guard<std::mutex> lock(idx->mu);
   DeviceGuard g(idx->device);
   B200_TRY(scratch_acquire(idx, (cudaStream_t)stream));
-  const int rc = search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, (cudaStream_t)stream);
+  int rc = B200_OK;
+  if (d_q && d_D && d_I && nq >= 1 && k >= 1 && ((uintptr_t)d_q & 15) == 0) {
+    if (idx->nlist > 0) B200_TRY(ivf_finalize(idx));
+    rc = search_graph(idx, d_q, nq, k, d_D, d_I, d_R, (cudaStream_t)stream);
+  }
+  if (rc == 0) rc = search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, (cudaStream_t)stream);
+  else if (rc == 1) rc = B200_OK;
   B200_TRY(scratch_release(idx, (cudaStream_t)stream));
   return rc;
 }
@@ -415,7 +505,7 @@ int b200_index_search(b200_index* idx, const float* h_q, int nq, int k, float* h
   float* d_R = h_R ? (float*)p : nullptr;
   B200_TRY(scratch_acquire(idx, 0));
   B200_CUDA(cudaMemcpyAsync(d_q, h_q, qb, cudaMemcpyHostToDevice, 0));
-  B200_TRY(search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, 0));
+  B200_TRY(search_device_impl(idx, d_q, nq, k, d_D, d_I, d_R, 0));   // legacy stream: never captured
   B200_TRY(scratch_release(idx, 0));
   B200_CUDA(cudaMemcpyAsync(h_D, d_D, db, cudaMemcpyDeviceToHost, 0));
   B200_CUDA(cudaMemcpyAsync(h_I, d_I, ib, cudaMemcpyDeviceToHost, 0));

@@ -485,12 +485,12 @@ int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned l
       idx->ev.push_back(a);
       idx->ev.push_back(b);
     }
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
+    B200_CUDA(index_record(idx, idx->ev[idx->ev_used], st));
     fn<<<(unsigned)((int64_t)qb * nprobe * segs), threads, smem, st>>>(
         reinterpret_cast<const uint4*>(idx->rows), cpr, d_q + (size_t)q0 * d, probes + (size_t)q0 * nprobe, nprobe, segs,
         idx->list_offsets, k, k1, M);
     B200_LAUNCH_OK();
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
+    B200_CUDA(index_record(idx, idx->ev[idx->ev_used + 1], st));
     idx->ev_used += 2;
     idx->last_scan_launches++;
     B200_TRY(launch_topk_select(k1, M, M, k, C, k2, (int64_t)slices * k, slices, qb, st));

@@ -506,7 +506,7 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
       idx->ev.push_back(a);
       idx->ev.push_back(b);
     }
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used], st));
+    B200_CUDA(index_record(idx, idx->ev[idx->ev_used], st));
     for (int qq = 0; qq < qb; qq += p.nqp) {
       const int valid = std::min(p.nqp, qb - qq);
       const float* qptr = d_q + (size_t)(q0 + qq) * d;
@@ -518,7 +518,7 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
       B200_LAUNCH_OK();
       idx->last_scan_launches++;
     }
-    B200_CUDA(cudaEventRecord(idx->ev[idx->ev_used + 1], st));
+    B200_CUDA(index_record(idx, idx->ev[idx->ev_used + 1], st));
     idx->ev_used += 2;
     // level 1: slices per query; level 2: one block per query
     topk_select_kernel<<<dim3(slices, qb), 1024, sel_smem, st>>>(k1, M1, M1, k, p.C, k2, (int64_t)slices * k);
