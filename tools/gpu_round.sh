@@ -9,6 +9,9 @@ if [ $rc -ne 0 ]; then export B200_ATTN_GEN=2; echo "falling back to attention_t
 timeout 600 python -m pytest tests/test_embed_gpu.py -q -k "embeddings_match or vit_l14" -p no:cacheprovider > gpurun_out/${tag}_fuse.log 2>&1
 rc=$?; echo "fused-LN embed tests rc=$rc" | tee -a gpurun_out/${tag}_fuse.log; tail -4 gpurun_out/${tag}_fuse.log
 if [ $rc -ne 0 ]; then export B200_FUSE_LN=0; echo "falling back to the separate LayerNorm kernel for the rest of this session"; fi
+timeout 400 python -m pytest tests/test_graphs_gpu.py -q -p no:cacheprovider > gpurun_out/${tag}_graphs.log 2>&1
+rc=$?; echo "graph tests rc=$rc" | tee -a gpurun_out/${tag}_graphs.log; tail -4 gpurun_out/${tag}_graphs.log
+if [ $rc -ne 0 ]; then export B200_GRAPHS=0; echo "falling back to eager launches for the rest of this session"; fi
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider --deselect tests/test_embed_gpu.py::test_tcgen05_attention_matches_fp32_reference > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log; tail -6 gpurun_out/${tag}_pytest.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
