@@ -125,6 +125,10 @@ PROTOTYPES = {
     "b200_preproc_create": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, C.POINTER(_vp)]),
     "b200_preproc_destroy": (_i, [_vp]),
     "b200_preproc_run": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "b200_jpeg_create": (_i, [_i, C.POINTER(_vp)]),
+    "b200_jpeg_destroy": (_i, [_vp]),
+    "b200_jpeg_info": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "b200_jpeg_decode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_mlp_create": (_i, [_i, _vp, _vp, _i, C.POINTER(_vp)]),
     "b200_mlp_destroy": (_i, [_vp]),
     "b200_mlp_load_layer": (_i, [_vp, _i, _vp, _vp]),

@@ -5,8 +5,8 @@
 returns the float32 `[n, 3, n_px, n_px]` batch on the device that `ClipMapper` / `encode_image`
 consume — bit-identical to torchvision's Compose[Resize(bicubic), CenterCrop, ToTensor, Normalize]
 on the host (tests/test_preprocess_gpu.py; pinned on the reference's own test_tensors fixtures).
-JPEG decoding stays where the reference does it (PIL in the DataLoader workers); what crosses PCIe is
-the decoded uint8 image instead of the resized float32 tensor."""
+`B200Preprocess.from_jpeg_bytes(list_of_bytes)` additionally decodes on the GPU (nvJPEG): what crosses PCIe is the
+compressed file.  Streams nvJPEG cannot parse fall back to PIL on the host, as the reference decodes every image."""
 import ctypes as C
 
 import numpy as np
@@ -64,6 +64,9 @@ class B200Preprocess:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib.b200_preproc_destroy(h)
+        j, self._jpeg = getattr(self, "_jpeg", None), None
+        if j:
+            lib.b200_jpeg_destroy(j)
 
     def pack(self, images):
         return pack_images(images)
@@ -89,3 +92,68 @@ class B200Preprocess:
         if not isinstance(images, (list, tuple)):
             images = [images]
         return self.run_packed(*self.pack(images), out=out)
+
+    # ---- JPEG bytes in (nvJPEG decode on the device) -----------------------------------------------------
+    def from_jpeg_bytes(self, blobs, out=None):
+        """blobs: list of bytes objects (JPEG files as read from disk / a tar shard, reader.py:98-106,158-165).
+        Returns float32 [n, 3, n_px, n_px] on the device.  Images nvJPEG cannot parse (CMYK, progressive streams on
+        some backends, non-JPEG files) are decoded with PIL on the host and uploaded as pixels."""
+        import io
+
+        n = len(blobs)
+        if getattr(self, "_jpeg", None) is None:
+            h = C.c_void_p()
+            check(lib.b200_jpeg_create(self.device.index or 0, C.byref(h)), "jpeg_create")
+            self._jpeg = h
+        bufs = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        heights = np.zeros(n, np.int32)
+        widths = np.zeros(n, np.int32)
+        host = {}
+        for i in range(n):   # per image, so that one unparsable stream does not fail the batch
+            pi = (C.c_void_p * 1)(ptrs[i])
+            si = (C.c_size_t * 1)(sizes[i])
+            if lib.b200_jpeg_info(self._jpeg, pi, si, 1, C.c_void_p(heights[i:].ctypes.data), C.c_void_p(widths[i:].ctypes.data)) != 0:
+                from PIL import Image
+
+                host[i] = to_rgb8(Image.open(io.BytesIO(blobs[i])))
+                heights[i], widths[i] = host[i].shape[0], host[i].shape[1]
+        nbytes = heights.astype(np.int64) * widths * 3
+        offsets = np.zeros(n, np.int64)
+        if n > 1:
+            offsets[1:] = np.cumsum(nbytes[:-1])
+        pixels = torch.empty(int(nbytes.sum()), dtype=torch.uint8, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        dev_idx = [i for i in range(n) if i not in host]
+        if dev_idx:
+            k = len(dev_idx)
+            p2 = (C.c_void_p * k)(*[ptrs[i] for i in dev_idx])
+            s2 = (C.c_size_t * k)(*[sizes[i] for i in dev_idx])
+            o2 = np.ascontiguousarray(offsets[dev_idx])
+            h2 = np.ascontiguousarray(heights[dev_idx])
+            w2 = np.ascontiguousarray(widths[dev_idx])
+            check(lib.b200_jpeg_decode(self._jpeg, p2, s2, k, C.c_void_p(pixels.data_ptr()), C.c_void_p(o2.ctypes.data),
+                                       C.c_void_p(h2.ctypes.data), C.c_void_p(w2.ctypes.data), C.c_void_p(stream)), "jpeg_decode")
+        for i, a in host.items():
+            pixels[offsets[i]:offsets[i] + nbytes[i]].copy_(torch.from_numpy(a.reshape(-1)))
+        return self.run_packed(pixels, offsets, heights, widths, out=out)
+
+    def decode_jpeg_bytes(self, blob):
+        """One JPEG file -> uint8 [H, W, 3] numpy (device decode, copied back): for tests and inspection."""
+        n = 1
+        if getattr(self, "_jpeg", None) is None:
+            h = C.c_void_p()
+            check(lib.b200_jpeg_create(self.device.index or 0, C.byref(h)), "jpeg_create")
+            self._jpeg = h
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        ptrs = (C.c_void_p * n)(buf.ctypes.data)
+        sizes = (C.c_size_t * n)(buf.size)
+        hh, ww = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        check(lib.b200_jpeg_info(self._jpeg, ptrs, sizes, 1, C.c_void_p(hh.ctypes.data), C.c_void_p(ww.ctypes.data)), "jpeg_info")
+        pixels = torch.empty(int(hh[0]) * int(ww[0]) * 3, dtype=torch.uint8, device=self.device)
+        off = np.zeros(1, np.int64)
+        check(lib.b200_jpeg_decode(self._jpeg, ptrs, sizes, 1, C.c_void_p(pixels.data_ptr()), C.c_void_p(off.ctypes.data),
+                                   C.c_void_p(hh.ctypes.data), C.c_void_p(ww.ctypes.data),
+                                   C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "jpeg_decode")
+        return pixels.cpu().numpy().reshape(int(hh[0]), int(ww[0]), 3)

@@ -261,6 +261,18 @@ int b200_preproc_destroy(b200_preproc* p);
 int b200_preproc_run(b200_preproc* p, const uint8_t* pixels, int pixels_on_device, const int64_t* h_offsets,
                      const int32_t* h_heights, const int32_t* h_widths, int n, float* d_out, void* stream);
 
+/* JPEG decode on the GPU in front of the transform (the reference decodes with PIL in its
+ * DataLoader workers, reader.py:98-106): nvJPEG (resolved with dlopen) decodes n host bitstreams into the packed
+ * RGB uint8 HWC device buffer b200_preproc_run takes with pixels_on_device = 1.  b200_jpeg_info gives the sizes
+ * (so the caller can lay out h_offsets) and fails on streams nvJPEG cannot parse — decode those on the host. */
+typedef struct b200_jpeg b200_jpeg;
+int b200_jpeg_create(int device, b200_jpeg** out);
+int b200_jpeg_destroy(b200_jpeg* j);
+int b200_jpeg_info(b200_jpeg* j, const uint8_t* const* h_streams, const size_t* h_sizes, int n, int32_t* h_heights,
+                   int32_t* h_widths);
+int b200_jpeg_decode(b200_jpeg* j, const uint8_t* const* h_streams, const size_t* h_sizes, int n, uint8_t* d_pixels,
+                     const int64_t* h_offsets, const int32_t* h_heights, const int32_t* h_widths, void* stream);
+
 /* ---- IVF training --------------------------------------------------------------
  * k-means for the coarse quantiser of b200_index_create_ivfflat: the GPU counterpart of the training
  * step behind `clip-retrieval index` (clip_retrieval/clip_index.py:12-31 -> autofaiss.build_index ->

@@ -78,3 +78,41 @@ def test_mapper_accepts_raw_images():
     via_host = mapper({"image_tensor": tens, "image_filename": ["a", "b", "c"]})["image_embs"]
     assert via_gpu.dtype == np.float16 and via_gpu.shape == via_host.shape
     assert np.array_equal(via_gpu, via_host)
+
+
+@pytest.mark.timeout(300)
+def test_gpu_jpeg_decode_feeds_the_transform():
+    """nvJPEG decode in front of the GPU transform (the reference decodes with PIL on the host, reader.py:98-106).
+    JPEG decoders are not bit-identical (IDCT rounding, chroma upsampling): bounded in grey levels against the
+    Pillow-decoded pixels of the same files, and in cosine on what the image tower makes of them."""
+    import torch
+    import clip_retrieval_b200 as m
+    from oracle import clip_ref
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(here, "jpeg_pixels.npz"))
+    names = ["a_444", "b_420", "c_gray"]
+    blobs = [open(os.path.join(here, "jpeg", n + ".jpg"), "rb").read() for n in names]
+    pre = m.B200Preprocess(224)
+    for n, blob in zip(names, blobs):
+        got = pre.decode_jpeg_bytes(blob)
+        want = gold[n]
+        assert got.shape == want.shape and got.dtype == np.uint8
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.mean() <= 1.5 and np.percentile(diff, 99) <= 8, (n, diff.mean(), np.percentile(diff, 99), diff.max())
+    # the batch path: decode + transform on the device, plus one non-JPEG blob that must fall back to the host decode
+    import io
+    from PIL import Image
+
+    png = io.BytesIO()
+    Image.fromarray(gold["a_444"]).save(png, format="PNG")
+    batch = pre.from_jpeg_bytes(blobs + [png.getvalue()])
+    ref = pre([gold[n] for n in names] + [gold["a_444"]])           # transform of the Pillow-decoded pixels
+    assert batch.shape == ref.shape == (4, 3, 224, 224)
+    assert torch.equal(batch[3], ref[3])                             # host-decoded fallback: identical pixels
+    assert float((batch[:3] - ref[:3]).abs().mean()) <= 0.03         # in units of the normalised tensor (1 level ~ 0.015)
+    cfg = clip_ref.CONFIGS["ViT-B/32"]
+    model = m.B200Clip(m.ARCHS["ViT-B/32"], device=0, max_batch=4).load_state_dict(clip_ref.make_state_dict(cfg, seed=0))
+    ea, eb = model.embed_image_device(batch), model.embed_image_device(ref)
+    cos = torch.nn.functional.cosine_similarity(ea.float(), eb.float(), dim=-1)
+    assert float(cos.min()) >= 0.999, cos
