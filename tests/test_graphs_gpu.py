@@ -75,7 +75,11 @@ def test_graph_replay_of_single_query_search_and_invalidation(kind):
         idx.nprobe = 4
         return idx
 
-    idx = make()
+    os.environ["B200_GRAPHS"] = "1"
+    try:
+        idx = make()
+    finally:
+        os.environ.pop("B200_GRAPHS", None)
     idx.add(X[:n])
     Q = synth_ref.rows_f32(8, d, seed=77, clustered=True, centroid_seed=7, nlist=nlist)
     qd = torch.from_numpy(Q).cuda()

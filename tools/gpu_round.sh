@@ -3,6 +3,8 @@
 # serving-shape launch list.  Everything lands in gpurun_out/<tag>_*.
 tag=${1:-r02}
 mkdir -p gpurun_out
+# new paths of this round are opt-in until verified: switch them on for this session, fall back one by one
+export B200_ATTN_GEN=3 B200_FUSE_LN=1 B200_GRAPHS=1
 timeout 600 python -m pytest tests/test_embed_gpu.py -q -k tcgen05 -p no:cacheprovider > gpurun_out/${tag}_attn.log 2>&1
 rc=$?; echo "attention tests rc=$rc" | tee -a gpurun_out/${tag}_attn.log; tail -4 gpurun_out/${tag}_attn.log
 if [ $rc -ne 0 ]; then export B200_ATTN_GEN=2; echo "falling back to attention_tc2 for the rest of this session"; fi
