@@ -20,3 +20,4 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 
 echo "bench rc=$?"; tail -c 1500 gpurun_out/${tag}_bench.err; head -c 1200 gpurun_out/${tag}_bench.json; echo
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_serve_launches.csv python tools/serve_shapes.py --reps 2 > gpurun_out/${tag}_serve.log 2>&1
 timeout 120 python tools/serve_shapes.py --reps 20 > gpurun_out/${tag}_serve_plain.log 2>&1; cat gpurun_out/${tag}_serve_plain.log
+timeout 400 python tools/chunk_sweep.py > gpurun_out/${tag}_chunk_sweep.log 2>&1; cat gpurun_out/${tag}_chunk_sweep.log
