@@ -10,15 +10,17 @@
 //     norm per row, and is known BEFORE the scores exist.  The pass also tracks the true row maximum; if a row's
 //     slack exceeds 64 the warp repeats the pass with the exact maximum (the scores are still in TMEM): results are
 //     those of the two-pass softmax in every case, the second read happens only for pathological rows.
-//  2. T = 257 = 2 * 128 + 1 is two tensor-core tiles plus ONE row: the leftover rows (T mod 128 <= 8) are computed by
-//     a dedicated warp on the FMA pipe straight from the K / V tiles in shared memory (exact two-pass softmax in
-//     registers), instead of a third 128-row tile that is 99 % padding.
+//  2. T = 257 = 2 * 128 + 1 is two tensor-core tiles plus ONE row: the leftover rows (T mod 128 <= 4) are computed on
+//     the FMA pipe by the 128 threads of the softmax group that owns the head's last tile, straight from the K / V
+//     tiles in shared memory (scores before the tile's own softmax, P.V after its output), instead of a third
+//     128-row tile that is 99 % padding.  (A first version gave them to one dedicated warp that held K and V until
+//     it was done: 2x slower than attention_tc2 — profiles/r02a.)
 //  3. tcgen05.ld of score chunk c+1 is in flight while chunk c is exponentiated (two register buffers).
 // Per-sample 3-D tensor maps (rows >= T of a box are zero-filled) keep a sample's boxes from reading its neighbour.
 //
 //   warp 8      TMA: K, V rows of the head (128-row boxes) once per (sample, head), Q tile per 128 query rows.
 //   warp 9      tcgen05.mma issuer: S(t) = Q K^T, O(t) = P V; order S(t), PV(t-1), S(t+1), PV(t), ...
-//   warp 10     per head: max_j |k_j| for the softmax bound, and the leftover query rows on the FMA pipe.
+//   (before)    attn_kmax_kernel: max_j |k_j| per (sample, head) for the softmax bound, one warp per head.
 //   warps 0..3  softmax group 0 (even tiles), warps 4..7 group 1 (odd tiles): thread = query row.
 #include "embed_kernels.cuh"
 #include "gemm.cuh"
@@ -31,9 +33,17 @@ constexpr int A3_MAXT = 264;                      // 256 keys on the tensor core
 constexpr int A3_Q_BYTES = 128 * 128;             // 16 KB
 constexpr int A3_KV_MAIN = 2 * 128 * 128;         // 256 rows x 128 B
 constexpr int A3_P_BYTES = 4 * 128 * 128;         // 4 key blocks of [128 rows x 64 keys] per group
-constexpr int A3_SMEM = A3_Q_BYTES + 2 * A3_KV_MAIN + 2 * A3_P_BYTES + 512 + 1024;
-constexpr int A3_THREADS = 352;
+constexpr int A3_TAIL_MAX = 4;                    // leftover query rows (T mod 128) handled on the FMA pipe
+constexpr int A3_TAIL_BYTES = (A3_TAIL_MAX * 264 + 4 * 64 + 16) * 4;   // per group: p[rows][264], partial O [4][64], reductions
+constexpr int A3_SMEM = A3_Q_BYTES + 2 * A3_KV_MAIN + 2 * A3_P_BYTES + 2 * A3_TAIL_BYTES + 512 + 1024;
+constexpr int A3_THREADS = 320;
 constexpr float A3_MAX_SLACK = 64.0f;             // log2 units; above it the pass is repeated with the exact maximum
+
+// barrier over the 128 threads of one softmax group (named barriers 1 and 2)
+__device__ __forceinline__ void a3_group_sync(int grp) {
+  if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 // 8 consecutive bf16 of a swizzled K/V row in shared memory -> fp32
 __device__ __forceinline__ void a3_unpack8(const uint4& u, float* f) {
@@ -43,7 +53,8 @@ __device__ __forceinline__ void a3_unpack8(const uint4& u, float* f) {
 
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat16* __restrict__ qkv,
-                     __nv_bfloat16* __restrict__ out, int B, int T, int heads, int w, float scale_log2e, int causal) {
+                     __nv_bfloat16* __restrict__ out, const float* __restrict__ kmax_head, int B, int T, int heads, int w,
+                     float scale_log2e, int causal) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -51,20 +62,19 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   uint8_t* sK = sQ + A3_Q_BYTES;               // rows 0..255
   uint8_t* sV = sK + A3_KV_MAIN;               // rows 0..255
   uint8_t* sP = sV + A3_KV_MAIN;               // [2 groups][4 key blocks][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A3_P_BYTES);
+  float* sTail = reinterpret_cast<float*>(sP + 2 * A3_P_BYTES);   // [2 groups][A3_TAIL_BYTES / 4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sTail) + 2 * A3_TAIL_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;
-  uint64_t* k_free = bars + 3;    // MMA commit (last S of the head) + warp 10
+  uint64_t* k_free = bars + 3;    // MMA commit (last S of the head) + the 4 warps of the last tile's softmax group
   uint64_t* v_full = bars + 4;
-  uint64_t* v_free = bars + 5;    // MMA commit (last P.V of the head) + warp 10
+  uint64_t* v_free = bars + 5;    // MMA commit (last P.V of the head) + the 4 warps of the last tile's softmax group
   uint64_t* s_full = bars + 6;    // [2]
   uint64_t* p_full = bars + 8;    // [2]
   uint64_t* o_full = bars + 10;   // [2]
   uint64_t* buf_free = bars + 12; // [2]
-  uint64_t* kn_full = bars + 14;  // [4]  max |k| of head `it` published in s_kn[it & 3]
-  float* s_kn = reinterpret_cast<float*>(bars + 18);   // [4]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_kn + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int keys_main = T < 256 ? (T + 15) / 16 * 16 : 256;  // keys on the tensor core (multiple of 16)
@@ -73,7 +83,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   // query rows: full/partial 128-row tiles on the tensor core, a leftover of <= 8 rows (after at least one full
   // tile) on the FMA pipe
   const int n_full = T / 128, rem = T - n_full * 128;
-  const bool tail_rows = rem > 0 && rem <= 8 && n_full >= 1;
+  const bool tail_rows = rem > 0 && rem <= A3_TAIL_MAX && n_full >= 1;
   const int q_tiles = tail_rows ? n_full : (T + 127) / 128;
   const int fma_rows = tail_rows ? rem : 0;
   const int items = B * heads;
@@ -82,15 +92,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
-      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, 2);
-      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 2);
+      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, 5);
+      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 5);
       for (int i = 0; i < 2; i++) {
         ptx::mbar_init(&s_full[i], 1);
         ptx::mbar_init(&p_full[i], 4);
         ptx::mbar_init(&o_full[i], 1);
         ptx::mbar_init(&buf_free[i], 4);
       }
-      for (int i = 0; i < 4; i++) ptx::mbar_init(&kn_full[i], 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -175,136 +184,6 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
       if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
     }
     __syncwarp();
-  } else if (warp == 10) {
-    // ---------------- per head: max |k| for the softmax bound; leftover query rows on the FMA pipe ----------------
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
-      const int b = item / heads, h = item - b * heads;
-      ptx::mbar_wait(k_full, it & 1);
-      // max_j |k_j|^2 over the keys of this head: main keys from shared memory (zero rows past T add nothing),
-      // extra keys (>= 256) from the qkv buffer
-      float kn2 = 0.f;
-      for (int j = lane; j < keys_main; j += 32) {
-        const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          float f[8];
-          a3_unpack8(*reinterpret_cast<const uint4*>(row + c * 16), f);   // chunk order is irrelevant for a norm
-#pragma unroll
-          for (int e = 0; e < 8; e++) acc = fmaf(f[e], f[e], acc);
-        }
-        kn2 = fmaxf(kn2, acc);
-      }
-      for (int e = lane; e < extra; e += 32) {
-        const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + 256 + e) * 3 * w + w + (size_t)h * A3_HD);
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          float f[8];
-          a3_unpack8(__ldg(kp + c), f);
-#pragma unroll
-          for (int e2 = 0; e2 < 8; e2++) acc = fmaf(f[e2], f[e2], acc);
-        }
-        kn2 = fmaxf(kn2, acc);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
-      if (lane == 0) {
-        s_kn[it & 3] = sqrtf(kn2) * 1.0001f + 1e-30f;   // rounding of the norms must not turn the bound into a non-bound
-        ptx::mbar_arrive(&kn_full[it & 3]);              // release semantics: s_kn is visible to the waiters
-      }
-      if (fma_rows > 0) {
-        ptx::mbar_wait(v_full, it & 1);
-        for (int fr = 0; fr < fma_rows; fr++) {
-          const int qrow = n_full * 128 + fr;
-          const int kmax = causal ? qrow : T - 1;           // last visible key
-          float qf[A3_HD];
-          const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + qrow) * 3 * w + (size_t)h * A3_HD);
-#pragma unroll
-          for (int c = 0; c < 8; c++) a3_unpack8(__ldg(qp + c), qf + c * 8);
-          // scores of keys lane, lane + 32, ... (9 per lane cover T <= 264 + slack)
-          float s[9];
-          float m = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 9; i++) {
-            const int j = i * 32 + lane;
-            float acc = -INFINITY;
-            if (j <= kmax) {
-              acc = 0.f;
-              if (j < 256) {
-                const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                  float f[8];
-                  a3_unpack8(*reinterpret_cast<const uint4*>(row + ((c ^ (j & 7)) * 16)), f);
-#pragma unroll
-                  for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
-                }
-              } else {
-                const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                  float f[8];
-                  a3_unpack8(__ldg(kp + c), f);
-#pragma unroll
-                  for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
-                }
-              }
-            }
-            s[i] = acc;
-            m = fmaxf(m, acc);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          const float mb = m * scale_log2e;
-          float l = 0.f;
-#pragma unroll
-          for (int i = 0; i < 9; i++) {
-            float p;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[i], scale_log2e, -mb)));
-            p = s[i] == -INFINITY ? 0.f : p;
-            // P is rounded to bf16 before it multiplies V, as on the tensor-core rows; the row sum uses the fp32 value
-            s[i] = __bfloat162float(__float2bfloat16_rn(p));
-            l += p;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-          // O[2 * lane, 2 * lane + 1] = sum_j p_j v_j
-          float o0 = 0.f, o1 = 0.f;
-          const int chunk = lane >> 2, within = (lane & 3) * 4;
-#pragma unroll
-          for (int i = 0; i < 9; i++) {
-            const int jend = min(32, kmax + 1 - i * 32);
-            for (int src = 0; src < jend; src++) {
-              const float pj = __shfl_sync(0xffffffffu, s[i], src);
-              const int j = i * 32 + src;
-              uint32_t v2;
-              if (j < 256) {
-                const uint8_t* row = sV + (j >> 7) * (128 * 128) + (j & 127) * 128;
-                v2 = *reinterpret_cast<const uint32_t*>(row + ((chunk ^ (j & 7)) * 16) + within);
-              } else {
-                v2 = __ldg(reinterpret_cast<const uint32_t*>(qkv + ((size_t)b * T + j) * 3 * w + 2 * w + (size_t)h * A3_HD) + lane);
-              }
-              const float2 vv = unpack_bf16x2(v2);
-              o0 = fmaf(pj, vv.x, o0);
-              o1 = fmaf(pj, vv.y, o1);
-            }
-          }
-          const float inv = 1.0f / l;
-          *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + qrow) * w + (size_t)h * A3_HD + 2 * lane) =
-              pack_bf16x2(o0 * inv, o1 * inv);
-        }
-      } else {
-        // no leftover rows: V is not read here, but the release barrier still counts this warp
-        ptx::mbar_wait(v_full, it & 1);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(k_free);
-        ptx::mbar_arrive(v_free);
-      }
-    }
   } else {
     // ---------------- softmax groups ----------------
     const int grp = warp >> 2;                     // 0: even tiles, 1: odd tiles
@@ -312,6 +191,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
     const int r = q4 * 32 + lane;                  // row inside the tile
     const uint32_t tbase = tmem_base + grp * 256 + ((uint32_t)(q4 * 32) << 16);
     uint8_t* sPg = sP + grp * A3_P_BYTES;
+    float* sTp = sTail + grp * (A3_TAIL_BYTES / 4);      // p of the leftover rows [A3_TAIL_MAX][264]
+    float* sTo = sTp + A3_TAIL_MAX * 264;                 // partial O of one leftover row [4 warps][64]
+    float* sTr = sTo + 4 * 64;                            // cross-warp reductions [8]
     const int chunks = (keys_main + 31) / 32;
     uint32_t tc = 0, it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
@@ -349,9 +231,82 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               if (ee == e) se[ee] = (256 + e <= kmax) ? acc : -INFINITY;
           }
         }
-        ptx::mbar_wait(&kn_full[it & 3], (it >> 2) & 1);
-        const float kn = *reinterpret_cast<volatile float*>(&s_kn[it & 3]);
+        const float kn = __ldg(kmax_head + item);
         float mb = sqrtf(qn2) * 1.0001f * kn * scale_log2e;      // >= every score of this row, in log2 units
+        // ---- leftover query rows of this head (T mod 128 <= 4): scores and probabilities now, while K is resident ----
+        const bool last_tile = mt == q_tiles - 1;
+        float tail_l[A3_TAIL_MAX];
+        if (last_tile) {
+          if (fma_rows > 0) {
+            ptx::mbar_wait(k_full, it & 1);
+            for (int fr = 0; fr < fma_rows; fr++) {
+              const int trow = n_full * 128 + fr;
+              const int tkmax = causal ? trow : T - 1;
+              float qf[A3_HD];
+              const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + trow) * 3 * w + (size_t)h * A3_HD);
+#pragma unroll
+              for (int c = 0; c < 8; c++) a3_unpack8(__ldg(qp + c), qf + c * 8);
+              // thread r: keys r, r + 128 from shared memory; key 256 + r (r < extra) from the qkv buffer
+              float sc[3];
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                const int j = u < 2 ? r + u * 128 : 256 + r;
+                float acc = -INFINITY;
+                if (j <= tkmax && (u < 2 ? j < keys_main : r < extra)) {
+                  acc = 0.f;
+                  if (u < 2) {
+                    const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                      float f[8];
+                      a3_unpack8(*reinterpret_cast<const uint4*>(row + ((c ^ (j & 7)) * 16)), f);
+#pragma unroll
+                      for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
+                    }
+                  } else {
+                    const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                      float f[8];
+                      a3_unpack8(__ldg(kp + c), f);
+#pragma unroll
+                      for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
+                    }
+                  }
+                }
+                sc[u] = acc;
+              }
+              // exact two-pass softmax over the 128 threads of the group
+              float mx = fmaxf(fmaxf(sc[0], sc[1]), sc[2]);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+              if (lane == 0) sTr[q4] = mx;
+              a3_group_sync(grp);
+              mx = fmaxf(fmaxf(sTr[0], sTr[1]), fmaxf(sTr[2], sTr[3]));
+              const float mbt = mx * scale_log2e;
+              float ls = 0.f;
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                float pv;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(sc[u], scale_log2e, -mbt)));
+                pv = sc[u] == -INFINITY ? 0.f : pv;
+                ls += pv;
+                const int j = u < 2 ? r + u * 128 : 256 + r;
+                // P is rounded to bf16 before it multiplies V, as on the tensor-core rows; the row sum keeps fp32
+                if (j < 264) sTp[fr * 264 + j] = __bfloat162float(__float2bfloat16_rn(pv));
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+              if (lane == 0) sTr[4 + q4] = ls;
+              a3_group_sync(grp);
+              tail_l[fr] = (sTr[4] + sTr[5]) + (sTr[6] + sTr[7]);
+              a3_group_sync(grp);   // sTr is reused by the next row
+            }
+          }
+          // K of this head is no longer needed by this group (the other group never reads it)
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(k_free);
+        }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
 
@@ -477,6 +432,52 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
             *reinterpret_cast<uint4*>(op + g * 8) = a;
           }
         }
+        // ---- leftover query rows: O = P V on the FMA pipe, V still resident; then V is released ----
+        if (last_tile) {
+          if (fma_rows > 0) {
+            ptx::mbar_wait(v_full, it & 1);
+            const int dp = lane;                              // dims 2 dp, 2 dp + 1
+            const int chunk = dp >> 2, within = (dp & 3) * 4;
+            for (int fr = 0; fr < fma_rows; fr++) {
+              const int trow = n_full * 128 + fr;
+              const int tkmax = causal ? trow : T - 1;
+              const float* pr = sTp + fr * 264;
+              float a0 = 0.f, a1 = 0.f;
+              // warp q4 of the group: keys [64 q4, 64 q4 + 64); warp 3 also the keys >= 256
+              const int j0 = q4 * 64, j1 = min(min(j0 + 64, keys_main), tkmax + 1);
+#pragma unroll 4
+              for (int j = j0; j < j1; j++) {
+                const uint8_t* row = sV + (j >> 7) * (128 * 128) + (j & 127) * 128;
+                const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + ((chunk ^ (j & 7)) * 16) + within));
+                const float pj = pr[j];
+                a0 = fmaf(pj, vv.x, a0);
+                a1 = fmaf(pj, vv.y, a1);
+              }
+              if (q4 == 3) {
+                for (int e = 0; e < extra; e++) {
+                  const int j = 256 + e;
+                  if (j > tkmax) break;
+                  const float2 vv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + ((size_t)b * T + j) * 3 * w + 2 * w + (size_t)h * A3_HD) + dp));
+                  const float pj = pr[j];
+                  a0 = fmaf(pj, vv.x, a0);
+                  a1 = fmaf(pj, vv.y, a1);
+                }
+              }
+              sTo[q4 * 64 + 2 * dp] = a0;
+              sTo[q4 * 64 + 2 * dp + 1] = a1;
+              a3_group_sync(grp);
+              if (q4 == 0) {
+                const float inv = 1.0f / tail_l[fr];
+                const float o0 = (sTo[2 * dp] + sTo[64 + 2 * dp]) + (sTo[128 + 2 * dp] + sTo[192 + 2 * dp]);
+                const float o1 = (sTo[2 * dp + 1] + sTo[64 + 2 * dp + 1]) + (sTo[128 + 2 * dp + 1] + sTo[192 + 2 * dp + 1]);
+                *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + trow) * w + (size_t)h * A3_HD + 2 * dp) = pack_bf16x2(o0 * inv, o1 * inv);
+              }
+              a3_group_sync(grp);   // sTo is reused by the next row
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(v_free);
+        }
       }
     }
   }
@@ -486,12 +487,40 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// max_j |k_j| (Euclidean norm of a key row of the head, times a hair for the rounding of the norms) per (sample, head):
+// the factor of the softmax bound that does not depend on the query.  One warp per head, the K third of the qkv buffer
+// read once (180 MB per ViT-L/14 layer at batch 1024, ~30 us).
+__global__ void __launch_bounds__(256)
+attn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int heads, int w, float* __restrict__ kmax_head) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= B * heads) return;
+  const int b = item / heads, h = item - b * heads;
+  float kn2 = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      float f[8];
+      a3_unpack8(__ldg(kp + c), f);
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc = fmaf(f[e], f[e], acc);
+    }
+    kn2 = fmaxf(kn2, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
+  if (lane == 0) kmax_head[item] = sqrtf(kn2) * 1.0001f + 1e-30f;
+}
+
 bool attention_tc3_supported(int T, int heads, int w) {
   return heads > 0 && w % heads == 0 && w / heads == A3_HD && T >= 1 && T <= A3_MAXT;
 }
 
-int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
-                  int causal, int sms, cudaStream_t st) {
+int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* kmax_scratch, int B, int T,
+                  int heads, int w, int causal, int sms, cudaStream_t st) {
+  B200_CHECK(kmax_scratch != nullptr, B200_ERR_INVALID, "attention_tc3: needs a [B * heads] fp32 scratch");
   B200_CHECK(attention_tc3_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc3: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
   if (B == 0) return B200_OK;
@@ -505,7 +534,9 @@ int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat1
   const float scale_log2e = (1.0f / sqrtf((float)A3_HD)) * 1.4426950408889634f;
   const int items = B * heads;
   const int grid = items < sms ? items : sms;
-  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, B, T, heads, w, scale_log2e, causal);
+  attn_kmax_kernel<<<(items + 7) / 8, 256, 0, st>>>(qkv, B, T, heads, w, kmax_scratch);
+  B200_LAUNCH_OK();
+  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, kmax_scratch, B, T, heads, w, scale_log2e, causal);
   B200_LAUNCH_OK();
   return B200_OK;
 }

@@ -25,7 +25,7 @@ struct Linear {
   float* b = nullptr;          // [N] or null (folded LayerNorm: d[n] = sum_k beta[k] W[n,k] + b[n])
   float* lnc = nullptr;        // folded LayerNorm: c[n] = sum_k W'[n,k], W' = bf16(W * gamma)  (gemm.cuh)
   int N = 0, K = 0;
-  CUtensorMap tm256, tm128;
+  CUtensorMap tm256, tm128, tm64, tm32;   // weight boxes of BN rows x 64 columns for every tile width
 };
 
 struct Layer {
@@ -46,6 +46,7 @@ struct Tower {
   __nv_bfloat16* vt = nullptr;
   CUtensorMap tm_qk, tm_vt;
   CUtensorMap tm_qkv3;   // per-sample 3-D map over qkv [max_batch, T, 3w] (attention_tc3.cu)
+  float* kmax = nullptr; // [max_batch * heads] max key norm per (sample, head): the softmax bound of attention_tc3.cu
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
   __nv_bfloat16* proj = nullptr;             // [width, D]
 };
@@ -74,6 +75,7 @@ struct b200_clip {
   __nv_bfloat16* tok_emb = nullptr;  // [vocab, w]
   float* tpos = nullptr;             // [ctx, w]
   int* pool_idx = nullptr;
+  float* feat = nullptr;             // raw projected features fp32 [min(max_batch, 128), D] (small-batch pool/projection split)
   // staging for the host entry points
   void* stage_in = nullptr;
   void* stage_out = nullptr;
@@ -127,6 +129,8 @@ static int make_linear(b200_clip* m, Linear* l, int N, int K, bool bias) {
   }
   B200_TRY(make_tmap_2d(&l->tm256, l->w, 1, N, K, K, 256, GEMM_BK));
   B200_TRY(make_tmap_2d(&l->tm128, l->w, 1, N, K, K, 128, GEMM_BK));
+  B200_TRY(make_tmap_2d(&l->tm64, l->w, 1, N, K, K, 64, GEMM_BK));
+  B200_TRY(make_tmap_2d(&l->tm32, l->w, 1, N, K, K, 32, GEMM_BK));
   return B200_OK;
 }
 
@@ -173,6 +177,7 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
     B200_TRY(make_tmap_2d(&t->tm_qk, t->qkv, 1, rows, 3 * (size_t)w, 3 * (size_t)w, 128, 64));
     B200_TRY(make_tmap_2d(&t->tm_vt, t->vt, 1, vt_rows, t->Tp, t->Tp, 64, 64));
     B200_TRY(make_tmap_3d(&t->tm_qkv3, t->qkv, 1, (uint64_t)m->cfg.max_batch, (uint64_t)T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128));
+    B200_TRY(dev_alloc(m, &t->kmax, (size_t)m->cfg.max_batch * c.heads));
   }
   return B200_OK;
 }
@@ -203,7 +208,8 @@ static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int
   const int bn = gemm_pick_bn(M, l.N, m->sms);
   ep.bias = l.b;
   m->last_launches++;
-  return gemm_bf16_launch(tmA, bn == 256 ? l.tm256 : l.tm128, bn, M, l.N, l.K, ep, m->sms, st);  // pair mode: tm128
+  const CUtensorMap& tmB = bn == 256 ? l.tm256 : (bn == 64 ? l.tm64 : (bn == 32 ? l.tm32 : l.tm128));   // pair mode: tm128
+  return gemm_bf16_launch(tmA, tmB, bn, M, l.N, l.K, ep, m->sms, st);
 }
 
 static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st) {
@@ -228,7 +234,7 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
-        B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+        B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st));
       else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
         B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
@@ -263,7 +269,7 @@ static int encode_image_chunk(b200_clip* m, const float* d_px, int B, void* d_ou
     B200_TRY(layernorm_rows(t.x, w, t.x, w, m->lnpre_g, m->lnpre_b, (int64_t)B * T, w, st)); }
   B200_TRY(run_blocks(m, t, B, 0, st));
   { SpanGuard sg(m, CLS_OTHER, st); m->last_launches++;
-    B200_TRY(pool_ln_proj_norm(t.x, T, w, nullptr, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st)); }
+    B200_TRY(pool_ln_proj_norm(t.x, T, w, nullptr, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st, m->feat)); }
   return B200_OK;
 }
 
@@ -276,7 +282,7 @@ static int encode_text_chunk(b200_clip* m, const int64_t* d_tok, int B, void* d_
     B200_TRY(token_argmax(d_tok, m->pool_idx, B, T, st)); }
   B200_TRY(run_blocks(m, t, B, 1, st));
   { SpanGuard sg(m, CLS_OTHER, st); m->last_launches++;
-    B200_TRY(pool_ln_proj_norm(t.x, T, w, m->pool_idx, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st)); }
+    B200_TRY(pool_ln_proj_norm(t.x, T, w, m->pool_idx, t.lnf_g, t.lnf_b, t.proj, m->cfg.embed_dim, d_out, out_f16, normalize, B, st, m->feat)); }
   return B200_OK;
 }
 
@@ -440,6 +446,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
     B200_TRY(dev_alloc(m, &m->tok_emb, (size_t)cfg->vocab_size * cfg->text.width));
     B200_TRY(dev_alloc(m, &m->tpos, (size_t)cfg->context_length * cfg->text.width));
     B200_TRY(dev_alloc(m, &m->pool_idx, (size_t)cfg->max_batch));
+    B200_TRY(dev_alloc(m, &m->feat, (size_t)std::min(cfg->max_batch, 128) * cfg->embed_dim));
     const size_t in_bytes = std::max((size_t)cfg->max_batch * 3 * cfg->image_size * cfg->image_size * 4,
                                      (size_t)cfg->max_batch * cfg->context_length * 8);
     B200_CUDA(cudaMalloc(&m->stage_in, in_bytes));
@@ -696,8 +703,13 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
   if (Tp == -2) {
     CUtensorMap t3;
     B200_TRY(make_tmap_3d(&t3, d_qkv, 1, (uint64_t)B, (uint64_t)T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128));
-    return attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
-                         (cudaStream_t)stream);
+    float* kmax = nullptr;
+    B200_CUDA(cudaMalloc((void**)&kmax, (size_t)std::max(1, B * heads) * 4));
+    const int rc = attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, kmax, B, T, heads, w, causal,
+                                 sm_count(device), (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);   // stand-alone test entry: the scratch dies here
+    cudaFree(kmax);
+    return rc;
   }
   // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu)
   if (Tp < 0)

@@ -33,12 +33,13 @@ int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloa
 // Third generation (attention_tc3.cu): one pass over the scores (Cauchy-Schwarz bound instead of the row maximum),
 // leftover query rows (T mod 128 <= 8) on the FMA pipe, per-sample 3-D tensor map tm3 over qkv [B, T, 3w], box 128x64.
 bool attention_tc3_supported(int T, int heads, int w);
-int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
-                  int causal, int sms, cudaStream_t st);
+int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* kmax_scratch /*[B*heads]*/,
+                  int B, int T, int heads, int w, int causal, int sms, cudaStream_t st);
 // K8/K10/K11: pooled row (x[b*T + pool_index(b)]) -> LN -> @ proj [w, D] -> optional L2 normalise
 // -> fp16 or fp32.  pool_idx == nullptr pools token 0 (vision); else row pool_idx[b] (text EOT).
 int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx, const float* gamma, const float* beta,
-                      const __nv_bfloat16* proj, int D, void* out, int out_f16, int normalize, int B, cudaStream_t st);
+                      const __nv_bfloat16* proj, int D, void* out, int out_f16, int normalize, int B, cudaStream_t st,
+                      float* feat_scratch = nullptr);   // fp32 [B, D]: batches <= 128 split the projection over D / 64 blocks
 // argmax(tokens, dim=-1) (first maximum) -> pool_idx[b]
 int token_argmax(const int64_t* tokens, int* pool_idx, int B, int T, cudaStream_t st);
 

@@ -73,8 +73,15 @@ void gemm_set_pair_mode(bool on) { g_pair_enabled = on; }
 int gemm_pick_bn(int M, int N, int sms) {
   const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
   if (g_pair_enabled && pair_tiles >= 2 * (long)(sms / 2) && N >= 256) return GEMM_MODE_PAIR;
+  const long mb = (M + GEMM_BM - 1) / GEMM_BM;
+  const long tiles128 = mb * ((N + 127) / 128);
+  if (tiles128 < sms && N >= 64) {
+    // serving shapes (a few row blocks): the GEMM is a weight read; spread it over as many SMs as there are tiles
+    const long tiles64 = mb * ((N + 63) / 64);
+    return tiles64 < sms ? 32 : 64;
+  }
   if (N % 256 != 0 && N % 128 == 0) return 128;
-  const long tiles256 = (long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256);
+  const long tiles256 = mb * ((N + 255) / 256);
   if (tiles256 < sms && N > 128) return 128;  // small problems: more, narrower tiles
   return 256;
 }
@@ -126,6 +133,8 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
   }
   if (bn == 256) return launch_bn<256>(tmA, tmB, M, N, K, ep, sms, st);
   if (bn == 128) return launch_bn<128>(tmA, tmB, M, N, K, ep, sms, st);
+  if (bn == 64) return launch_bn<64>(tmA, tmB, M, N, K, ep, sms, st);
+  if (bn == 32) return launch_bn<32>(tmA, tmB, M, N, K, ep, sms, st);
   set_error("gemm: unsupported column block %d", bn);
   return B200_ERR_INVALID;
 }

@@ -110,7 +110,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 256 + 1024;  // ring + bias + LN c + barriers + align slack
-  static constexpr int TMEM_COLS = 2 * BN;                                         // 512 or 256
+  static constexpr int TMEM_COLS = 2 * BN;                                         // 512, 256, 128 or 64 (power of two >= 32)
+  // narrow tiles (BN = 64 / 32) exist for the serving shapes: with M <= 128 rows a GEMM has N / BN tiles in total, and
+  // the weight read (the whole cost at batch 1) is spread over that many SMs — 6 SMs at BN = 128 for N = 768
 };
 
 __device__ __forceinline__ void gemm_tile_coords(int tile, int mb, int nb, int& m_blk, int& n_blk) {
@@ -339,7 +341,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       EpiRow er = epi_row(ep, row, n0);
       if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
       float st_k = 0.f, st_s = 0.f, st_q = 0.f;
-      constexpr int CPW = BN / 64;   // 32-column chunks per epilogue warp
+      constexpr int CPW = BN >= 64 ? BN / 64 : 1;   // 32-column chunks per epilogue warp
+      if (half * CPW * 32 >= BN) {
+        // BN = 32: the second warp of each lane quarter has no columns; it only takes part in the hand-shake
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       uint4 res[CPW][4];
 #pragma unroll
       for (int ci = 0; ci < CPW; ci++) {

@@ -473,7 +473,8 @@ int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned l
     int segs = (int)std::min<int64_t>(32, std::max<int64_t>(1, (2 * idx->sms + (int64_t)qb * nprobe - 1) / ((int64_t)qb * nprobe)));
     segs = (int)std::max<int64_t>(1, std::min<int64_t>(segs, (idx->max_list + 255) / 256));
     const int64_t M = (int64_t)nprobe * segs * nwarps * k;
-    int slices = (int)std::min<int64_t>(16, std::max<int64_t>(1, M / (4 * (int64_t)(C - k))));
+    int slices = (int)std::min<int64_t>(256, std::max<int64_t>(1, (M + C - 1) / C));   // one sort round per block
+    const int C2 = std::min(C, std::max(next_pow2(2 * k), next_pow2(slices * k)));
     void* w0 = nullptr;
     B200_TRY(index_ws(idx, 0, ((size_t)qb * M + (size_t)qb * slices * k) * 8, &w0));
     unsigned long long* k1 = (unsigned long long*)w0;
@@ -494,7 +495,7 @@ int ivf_search_keys(b200_index* idx, const float* d_q, int nq, int k, unsigned l
     idx->ev_used += 2;
     idx->last_scan_launches++;
     B200_TRY(launch_topk_select(k1, M, M, k, C, k2, (int64_t)slices * k, slices, qb, st));
-    B200_TRY(launch_topk_select(k2, (int64_t)slices * k, (int64_t)slices * k, k, C, d_keys + (size_t)q0 * k, k, 1, qb, st));
+    B200_TRY(launch_topk_select(k2, (int64_t)slices * k, (int64_t)slices * k, k, C2, d_keys + (size_t)q0 * k, k, 1, qb, st));
   }
   return B200_OK;
 }

@@ -485,7 +485,10 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
   B200_TRY(plan_scan(idx, k, nq, &p));
   const int64_t total_warps = (int64_t)p.grid * p.warps_out;
   const int64_t M1 = total_warps * k;
-  int slices = (int)std::min<int64_t>(64, std::max<int64_t>(1, M1 / (4 * (int64_t)(p.C - k))));
+  // level 1: one sort round per block (a block sorts one C-entry chunk of the candidates) — the select of a single
+  // query is latency, not throughput: 5 blocks x 5 dependent sort rounds took 98 us at nq = 1 (profiles/r02a)
+  int slices = (int)std::min<int64_t>(256, std::max<int64_t>(1, (M1 + p.C - 1) / p.C));
+  const int C2 = std::min(p.C, std::max(next_pow2(2 * k), next_pow2(slices * k)));   // level 2 buffer: slices * k keys
   const int QB = 64;  // queries per batch (bounds the scratch)
   const size_t keys1 = (size_t)QB * M1, keys2 = (size_t)QB * slices * k;
   void* ws = nullptr;
@@ -523,8 +526,8 @@ int scan_topk_keys(b200_index* idx, const __half* rows, int64_t n, const float* 
     // level 1: slices per query; level 2: one block per query
     topk_select_kernel<<<dim3(slices, qb), 1024, sel_smem, st>>>(k1, M1, M1, k, p.C, k2, (int64_t)slices * k);
     B200_LAUNCH_OK();
-    topk_select_kernel<<<dim3(1, qb), 1024, sel_smem, st>>>(k2, (int64_t)slices * k, (int64_t)slices * k, k, p.C,
-                                                            d_keys_out + (size_t)q0 * k, k);
+    topk_select_kernel<<<dim3(1, qb), 1024, (size_t)C2 * 8, st>>>(k2, (int64_t)slices * k, (int64_t)slices * k, k, C2,
+                                                                 d_keys_out + (size_t)q0 * k, k);
     B200_LAUNCH_OK();
   }
   return B200_OK;
