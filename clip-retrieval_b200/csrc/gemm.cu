@@ -171,6 +171,10 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   static const bool no_ldtm = false;
 #endif
   if (no_ldtm && bn == GEMM_MODE_PAIR) ep.exp_skip_tmem = 1;
+#ifdef B200_TIMING_EXPERIMENTS
+  static const bool no_store = getenv("B200_GEMM_NOSTORE") != nullptr;   // timing experiment: epilogue without global stores
+  if (no_store) ep.exp_skip_store = 1;
+#endif
   ep.bias = d_bias;
   ep.residual = (const __nv_bfloat16*)d_residual;
   ep.res_ld = N;
