@@ -161,7 +161,7 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
   B200_TRY(make_tmap_2d(&t->tm_a, t->a, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_f, t->f, 1, rows, c.mlp, c.mlp, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_x, t->x, 1, rows, w, w, GEMM_BM, GEMM_BK));
-  if (m->fuse_ln && w % 64 == 0) {
+  if (m->fuse_ln && w % 64 == 0 && w <= 64 * LN_MAX_SLOTS) {
     B200_TRY(dev_alloc(m, &t->stats, rows * (size_t)(w / 64)));
     for (auto& L : t->L) {
       B200_TRY(dev_alloc(m, &L.qkv.lnc, (size_t)3 * w));
