@@ -703,13 +703,20 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
   if (Tp == -2) {
     CUtensorMap t3;
     B200_TRY(make_tmap_3d(&t3, d_qkv, 1, (uint64_t)B, (uint64_t)T, 3 * (uint64_t)w, 3 * (uint64_t)w, 128));
-    float* kmax = nullptr;
-    B200_CUDA(cudaMalloc((void**)&kmax, (size_t)std::max(1, B * heads) * 4));
-    const int rc = attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, kmax, B, T, heads, w, causal,
-                                 sm_count(device), (cudaStream_t)stream);
-    cudaStreamSynchronize((cudaStream_t)stream);   // stand-alone test entry: the scratch dies here
-    cudaFree(kmax);
-    return rc;
+    // stand-alone test / timing entry: a grow-only scratch per device, kept for the life of the process
+    static std::mutex smu;
+    static float* scratch[64] = {};
+    static size_t scratch_n[64] = {};
+    std::lock_guard<std::mutex> lock(smu);
+    const size_t need = (size_t)std::max(1, B * heads);
+    if (scratch_n[device & 63] < need) {
+      if (scratch[device & 63]) { cudaDeviceSynchronize(); cudaFree(scratch[device & 63]); }
+      scratch[device & 63] = nullptr;
+      B200_CUDA(cudaMalloc((void**)&scratch[device & 63], need * 4));
+      scratch_n[device & 63] = need;
+    }
+    return attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, scratch[device & 63], B, T, heads, w, causal,
+                         sm_count(device), (cudaStream_t)stream);
   }
   // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu)
   if (Tp < 0)
