@@ -39,6 +39,7 @@ struct Tower {
   // activations
   __nv_bfloat16 *x = nullptr, *h = nullptr, *qkv = nullptr, *a = nullptr, *f = nullptr;
   CUtensorMap tm_h, tm_a, tm_f, tm_x;
+  CUtensorMap ts_x, ts_qkv, ts_f;   // store / residual maps (boxes of 32 rows x 64 columns) over x, qkv, f
   float2* stats = nullptr;     // folded LayerNorm: (mean, M2) per 64-column slot of every row of x
   // tcgen05 attention (head dim 64, T <= 320): V^T buffer + maps over qkv / V^T
   bool use_tc_attn = false;
@@ -69,6 +70,7 @@ struct b200_clip {
   __nv_bfloat16* cols = nullptr;  // [max_batch*g*g, Kp]
   CUtensorMap tm_cols;
   __nv_bfloat16* vpos = nullptr;  // positional_embedding bf16 [T, w] (residual operand of the patch GEMM)
+  CUtensorMap ts_vpos;            // its residual map (boxes of 32 rows x 64 columns)
   float* cls_pos0 = nullptr;      // class_embedding + positional_embedding[0]
   float *lnpre_g = nullptr, *lnpre_b = nullptr;
   // text front end
@@ -161,6 +163,9 @@ static int make_tower(b200_clip* m, Tower* t, const b200_tower_config& c, int T,
   B200_TRY(make_tmap_2d(&t->tm_a, t->a, 1, rows, w, w, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_f, t->f, 1, rows, c.mlp, c.mlp, GEMM_BM, GEMM_BK));
   B200_TRY(make_tmap_2d(&t->tm_x, t->x, 1, rows, w, w, GEMM_BM, GEMM_BK));
+  B200_TRY(make_tmap_2d(&t->ts_x, t->x, 1, rows, w, w, 32, 64));
+  B200_TRY(make_tmap_2d(&t->ts_qkv, t->qkv, 1, rows, 3 * (size_t)w, 3 * (size_t)w, 32, 64));
+  B200_TRY(make_tmap_2d(&t->ts_f, t->f, 1, rows, c.mlp, c.mlp, 32, 64));
   if (m->fuse_ln && w % 64 == 0 && w <= 64 * LN_MAX_SLOTS) {
     B200_TRY(dev_alloc(m, &t->stats, rows * (size_t)(w / 64)));
     for (auto& L : t->L) {
@@ -203,13 +208,13 @@ struct SpanGuard {
 };
 
 static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int M, GemmEpilogue ep, cudaStream_t st,
-                      int kind = CLS_GEMM) {
+                      int kind = CLS_GEMM, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr) {
   SpanGuard sg(m, kind, st);
   const int bn = gemm_pick_bn(M, l.N, m->sms);
   ep.bias = l.b;
   m->last_launches++;
   const CUtensorMap& tmB = bn == 256 ? l.tm256 : (bn == 64 ? l.tm64 : (bn == 32 ? l.tm32 : l.tm128));   // pair mode: tm128
-  return gemm_bf16_launch(tmA, tmB, bn, M, l.N, l.K, ep, m->sms, st);
+  return gemm_bf16_launch(tmA, tmB, bn, M, l.N, l.K, ep, m->sms, st, tmC, tmR);
 }
 
 static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st) {
@@ -231,7 +236,7 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     if (t.use_tc_attn && !m->attn_v_direct) {
       e1.vt = t.vt; e1.vt_col0 = 2 * w; e1.vt_T = t.T; e1.vt_Tp = t.Tp; e1.vt_hd = 64; e1.vt_heads = t.heads;
     }
-    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.qkv, M, e1, st, CLS_G_QKV));
+    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.qkv, M, e1, st, CLS_G_QKV, &t.ts_qkv));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
         B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st));
@@ -241,15 +246,15 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
     if (fused) e2.stats_out = t.stats;
-    B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st, CLS_G_OUT));
+    B200_TRY(run_linear(m, t.tm_a, L.out, M, e2, st, CLS_G_OUT, &t.ts_x, &t.ts_x));
     if (!fused) { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
       B200_TRY(layernorm_rows(t.x, w, t.h, w, L.ln2_g, L.ln2_b, M, w, st)); }
     GemmEpilogue e3; e3.out = t.f; e3.out_ld = t.mlp; e3.act = act;
     if (fused) { e3.ln_stats = t.stats; e3.ln_c = L.fc.lnc; e3.ln_w = w; }
-    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.fc, M, e3, st, CLS_G_FC));
+    B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.fc, M, e3, st, CLS_G_FC, &t.ts_f));
     GemmEpilogue e4; e4.out = t.x; e4.out_ld = w; e4.residual = t.x; e4.res_ld = w;
     if (fused) e4.stats_out = t.stats;
-    B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st, CLS_G_PROJ));
+    B200_TRY(run_linear(m, t.tm_f, L.proj, M, e4, st, CLS_G_PROJ, &t.ts_x, &t.ts_x));
   }
   return B200_OK;
 }
@@ -264,7 +269,7 @@ static int encode_image_chunk(b200_clip* m, const float* d_px, int B, void* d_ou
   // patch embedding: x[b*T + 1 + p, :] = cols[b*g*g + p, :] · conv^T + positional_embedding[1 + p]
   GemmEpilogue ep; ep.out = t.x; ep.out_ld = w; ep.out_group = g * g;
   ep.residual = m->vpos; ep.res_ld = w; ep.res_row_mod = g * g; ep.res_row_off = 1;
-  B200_TRY(run_linear(m, m->tm_cols, m->conv, B * g * g, ep, st));
+  B200_TRY(run_linear(m, m->tm_cols, m->conv, B * g * g, ep, st, CLS_GEMM, &t.ts_x, &m->ts_vpos));
   { SpanGuard sg(m, CLS_LN, st); m->last_launches++;
     B200_TRY(layernorm_rows(t.x, w, t.x, w, m->lnpre_g, m->lnpre_b, (int64_t)B * T, w, st)); }
   B200_TRY(run_blocks(m, t, B, 0, st));
@@ -440,6 +445,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
     B200_CUDA(cudaMemset(m->cols, 0, prow * m->Kp * 2));
     B200_TRY(make_tmap_2d(&m->tm_cols, m->cols, 1, prow, m->Kp, m->Kp, GEMM_BM, GEMM_BK));
     B200_TRY(dev_alloc(m, &m->vpos, (size_t)T * cfg->vision.width));
+    B200_TRY(make_tmap_2d(&m->ts_vpos, m->vpos, 1, (uint64_t)T, (uint64_t)cfg->vision.width, (uint64_t)cfg->vision.width, 32, 64));
     B200_TRY(dev_alloc(m, &m->cls_pos0, (size_t)cfg->vision.width));
     B200_TRY(dev_alloc(m, &m->lnpre_g, (size_t)cfg->vision.width));
     B200_TRY(dev_alloc(m, &m->lnpre_b, (size_t)cfg->vision.width));

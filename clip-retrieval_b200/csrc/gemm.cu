@@ -67,6 +67,13 @@ int make_tmap_3d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t n2,
 
 static bool g_pair_enabled = true;
 void gemm_set_pair_mode(bool on) { g_pair_enabled = on; }
+// pair kernel: results through shared memory + TMA stores (B200_GEMM_TMA_STORE=0/1; default in gemm_tma_store_default)
+static bool gemm_tma_store_default() {
+  const char* e = getenv("B200_GEMM_TMA_STORE");
+  return e ? atoi(e) != 0 : false;   // opt-in until verified on hardware
+}
+static bool g_tma_store = gemm_tma_store_default();
+void gemm_set_tma_store(bool on) { g_tma_store = on; }
 
 // Column-block choice; GEMM_MODE_PAIR (= 512) selects the CTA-pair kernel (256x256 tiles over two
 // SMs, B operand through the 128-row tensor map) for problems that fill the chip with such tiles.
@@ -106,7 +113,7 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
 }
 
 int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int M, int N, int K,
-                     const GemmEpilogue& ep, int sms, cudaStream_t st) {
+                     const GemmEpilogue& ep, int sms, cudaStream_t st, const CUtensorMap* tmC, const CUtensorMap* tmR) {
   B200_CHECK(M >= 1 && N >= 8 && K >= 8 && N % 8 == 0 && K % 8 == 0, B200_ERR_INVALID,
              "gemm: need M>=1 and N, K multiples of 8 (M=%d N=%d K=%d)", M, N, K);
   B200_CHECK(ep.out != nullptr && ep.out_ld % 8 == 0 && ((uintptr_t)ep.out & 15) == 0, B200_ERR_INVALID,
@@ -122,13 +129,24 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
     if (!(configured.load() >> (dev & 63) & 1ull)) {
-      B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     G2_SMEM_BYTES));
+      B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     G2Cfg<false>::SMEM_BYTES));
+      B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     G2Cfg<true>::SMEM_BYTES));
       configured.fetch_or(1ull << (dev & 63));
     }
     const long tiles = (long)((M + G2_BM - 1) / G2_BM) * ((N + G2_BN - 1) / G2_BN);
     const int pairs = (int)std::min<long>(tiles, sms / 2);
-    gemm_bf16_tcgen05_pair_kernel<<<2 * pairs, GEMM_THREADS, G2_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep);
+    // results through shared memory + TMA stores when the caller provides the output (and residual) tensor maps
+    const bool tma_st = g_tma_store && tmC != nullptr && ep.vt == nullptr && (ep.residual == nullptr || tmR != nullptr);
+    if (tma_st) {
+      GemmEpilogue e2 = ep;
+      e2.tma_store = 1;
+      gemm_bf16_tcgen05_pair_kernel<true><<<2 * pairs, GEMM_THREADS, G2Cfg<true>::SMEM_BYTES, st>>>(
+          tmA, tmB, *tmC, ep.residual ? *tmR : *tmC, M, N, K, e2);
+    } else {
+      gemm_bf16_tcgen05_pair_kernel<false><<<2 * pairs, GEMM_THREADS, G2Cfg<false>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, M, N, K, ep);
+    }
     B200_LAUNCH_OK();
     return B200_OK;
   }
@@ -189,7 +207,7 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
     B200_CUDA(cudaMalloc((void**)&d, 32));
     B200_CUDA(cudaMemsetAsync(d, 0, 32, (cudaStream_t)stream));
     ep.dbg = d;
-    int rc = gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream);
+    int rc = gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream, nullptr, nullptr);
     unsigned long long h[4] = {0, 0, 0, 0};
     B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     B200_CUDA(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
@@ -200,7 +218,19 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
             100.0 * h[3] / (double)h[2]);
     return rc;
   }
-  return gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream);
+  CUtensorMap tmC, tmR;
+  const bool st_maps = bn == GEMM_MODE_PAIR && N >= 64;
+  if (st_maps) {
+    B200_TRY(make_tmap_2d(&tmC, d_C, 1, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64));
+    if (d_residual) B200_TRY(make_tmap_2d(&tmR, d_residual, 1, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64));
+  }
+  return gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream, st_maps ? &tmC : nullptr,
+                          (st_maps && d_residual) ? &tmR : nullptr);
+}
+
+extern "C" int b200_gemm_set_tma_store(int on) {
+  b200::gemm_set_tma_store(on != 0);
+  return B200_OK;
 }
 
 extern "C" int b200_gemm_set_pair_mode(int on) {

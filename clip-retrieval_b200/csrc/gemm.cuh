@@ -43,6 +43,7 @@ struct GemmEpilogue {
   int64_t out_ld = 0;
   int out_group = 0;                        // > 0: out row = (row / g) * (g + 1) + 1 + row % g  (cls slot)
   int act = ACT_NONE;
+  int tma_store = 0;                        // pair kernel: results leave through shared memory and TMA stores (gemm2.cuh)
   // LayerNorm folded into this GEMM (K5/K6 of SURVEY §2.2 without a separate normalisation pass): A is the RAW
   // residual stream x and the weights carry gamma (W'[n,k] = W[n,k] * gamma[k]), so
   //   LN(x) W^T + b = rstd * (x W'^T - mean * c) + d,   c[n] = sum_k W'[n,k],  d[n] = sum_k beta[k] W[n,k] + b[n].
@@ -205,6 +206,42 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow&
       st_q = fmaf(e[j], e[j], st_q);
     }
   }
+}
+
+// The eight finished values of columns col..col+7 of this thread's row (bias / folded LayerNorm, activation, residual
+// given as 8 packed bf16 in `rr`), packed to bf16; optional row-statistics accumulation as in epi_store8.
+__device__ __forceinline__ uint4 epi_pack8(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r8, const float* s_bias,
+                                           const float* s_c, int col, bool has_res, const uint4& rr, float st_k, float& st_s,
+                                           float& st_q) {
+  float v[8];
+  if (ep.ln_stats != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), ep.act);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+  }
+  if (has_res) {
+    const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z), dd = unpack_bf16x2(rr.w);
+    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+    v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  if (ep.stats_out != nullptr) {
+    const float2 f0 = unpack_bf16x2(o.x), f1 = unpack_bf16x2(o.y), f2 = unpack_bf16x2(o.z), f3 = unpack_bf16x2(o.w);
+    const float e[8] = {f0.x - st_k, f0.y - st_k, f1.x - st_k, f1.y - st_k, f2.x - st_k, f2.y - st_k, f3.x - st_k, f3.y - st_k};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      st_s += e[j];
+      st_q = fmaf(e[j], e[j], st_q);
+    }
+  }
+  return o;
 }
 
 // One 32-column chunk `c` of the tile for this thread's row: the four 8-column groups, and (stats_out) the
@@ -411,11 +448,15 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t row
                  uint32_t box_rows, uint32_t box_cols);
 int make_tmap_3d(CUtensorMap* out, const void* ptr, int dtype_bf16, uint64_t n2, uint64_t n1, uint64_t n0, uint64_t ld_elems,
                  uint32_t box_rows);
+// tmC / tmR (optional): maps over the output / residual matrices with boxes of 32 rows x 64 columns; when given, the
+// pair kernel stores through shared memory + TMA (and prefetches the residual tile the same way).
 int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int M, int N, int K,
-                     const GemmEpilogue& ep, int sms, cudaStream_t st);
+                     const GemmEpilogue& ep, int sms, cudaStream_t st, const CUtensorMap* tmC = nullptr,
+                     const CUtensorMap* tmR = nullptr);
 // Pick the column-block width for a GEMM with N output columns (256, or 128 when N % 256 != 0 or the
 // grid would be under-filled).
 int gemm_pick_bn(int M, int N, int sms);
 void gemm_set_pair_mode(bool on);
+void gemm_set_tma_store(bool on);
 
 }  // namespace b200

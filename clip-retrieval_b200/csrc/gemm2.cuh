@@ -19,27 +19,44 @@ namespace b200 {
 
 constexpr int G2_BM = 256;          // rows per pair tile (128 per CTA)
 constexpr int G2_BN = 256;
-constexpr int G2_STAGES = 6;   // 7 stages (224 KB) measured no better: the issuer waits for operands ~20-28% either way
+// Two variants.  TMAST = false: 6-stage ring, results stored from registers (16 B per thread and row).  TMAST = true
+// (production): 5-stage ring + 64 KB of staging — every epilogue warp owns two 32-row x 64-column boxes (128-byte
+// swizzle); the residual tile is PREFETCHED into them by TMA before the accumulator is ready, results overwrite it in
+// place and leave through cp.async.bulk.tensor stores.  Why: with register stores each warp instruction touches 32
+// different rows (32 half-used sectors); the LSU work of one tile was ~12 % of the K=1024 GEMMs and the per-thread
+// residual loads another 20 % of out-proj (tools/gemm_exp.sh, profiles/r02b_gemm_exp.txt).
+template <bool TMAST> struct G2Cfg {
+  static constexpr int STAGES = TMAST ? 5 : 6;   // 7 stages (224 KB) measured no better than 6
+  static constexpr int STAGING = TMAST ? 8 * 2 * 4096 : 0;
+  static constexpr int ALIGN_SLACK = TMAST ? 768 : 1024;   // dynamic shared memory starts 1024-aligned in practice; checked
+  static constexpr int SMEM_BYTES = STAGES * (2 * 128 * GEMM_BK * 2) + STAGING + 2 * 256 * 4 + 256 + ALIGN_SLACK;
+};
 constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;   // 16 KB (half of the 256-wide B tile)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 2 * G2_BN * 4 + 256 + 1024;
 
+template <bool TMAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M,
                               int N, int K, GemmEpilogue ep) {
+  constexpr int G2_STAGES = G2Cfg<TMAST>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
-  uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  if (TMAST && pad > (uint32_t)G2Cfg<TMAST>::ALIGN_SLACK) __trap();   // never on sm_100 (the dynamic window starts at 1024)
+  uint8_t* base = smem_raw + pad;
   uint8_t* sA = base;
   uint8_t* sB = base + G2_STAGES * G2_A_BYTES;
-  float* s_bias = reinterpret_cast<float*>(base + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* sStage = base + G2_STAGES * G2_STAGE_BYTES;                  // [8 warps][2 boxes][32 rows x 128 B]
+  float* s_bias = reinterpret_cast<float*>(sStage + G2Cfg<TMAST>::STAGING);
   float* s_c = s_bias + G2_BN;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_c + G2_BN);
   uint64_t* empty = full + G2_STAGES;
   uint64_t* tfull = empty + G2_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = tempty + 2;                                           // [8] residual boxes landed (one per epilogue warp)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(rbar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -51,6 +68,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   if (warp == GEMM_WARP_TMA && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (TMAST) {
+      ptx::prefetch_tensormap(&tmC);
+      ptx::prefetch_tensormap(&tmR);
+    }
   }
   if (warp == GEMM_WARP_MMA) {
     if (lane == 0) {
@@ -62,6 +83,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         ptx::mbar_init(&tfull[a], 1);
         ptx::mbar_init(&tempty[a], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
       }
+      for (int i = 0; i < 8; i++) ptx::mbar_init(&rbar[i], 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -149,6 +171,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     const int half = warp >> 2;        // which half of the tile columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t rphase = 0;
     const uint32_t tempty0_remote = ptx::mapa_u32(ptx::smem_u32(&tempty[0]), 0);
     for (int tile = pair; tile < tiles; tile += npairs) {
       int m_blk, n_blk;
@@ -168,6 +191,85 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
       float st_k = 0.f, st_s = 0.f, st_q = 0.f;
       constexpr int CPW = G2_BN / 64;   // 32-column chunks per epilogue warp
+      if constexpr (TMAST) {
+        // ---- results through shared memory and TMA stores ----
+        uint8_t* stage = sStage + warp * 8192;                 // two boxes of 32 rows x 64 columns (128 B rows, swizzled)
+        const int row0 = m_blk * G2_BM + (int)rank * 128 + q * 32;      // first row of this warp's slab
+        const int col0 = n0 + half * 128;                                // first column of this warp's half tile
+        const bool has_res = ep.residual != nullptr;
+        int out_row0 = row0, res_row0 = row0;
+        if (ep.out_group > 0) out_row0 = (row0 / ep.out_group) * (ep.out_group + 1) + 1 + row0 % ep.out_group;
+        if (ep.res_row_mod > 0) res_row0 = ep.res_row_off + row0 % ep.res_row_mod;
+        // the boxes are free once the stores of the previous tile have read them
+        if (lane == 0) ptx::bulk_wait_group_read<0>();
+        __syncwarp();
+        if (has_res && lane == 0 && row0 < M) {
+          // residual prefetch: both boxes in flight while the main loop of this tile runs
+          ptx::mbar_arrive_expect_tx(&rbar[warp], 8192);
+          ptx::tma_load_2d(stage, &tmR, &rbar[warp], col0, res_row0);
+          ptx::tma_load_2d(stage + 4096, &tmR, &rbar[warp], col0 + 64, res_row0);
+        }
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after();
+        if (has_res && row0 < M) ptx::mbar_wait(&rbar[warp], rphase);
+#pragma unroll
+        for (int ci = 0; ci < CPW; ci++) {
+          const int c = half * CPW + ci;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          ptx::tmem_ld_wait();
+          if (ci == CPW - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&tempty[acc]);
+              else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
+            }
+          }
+          if (ep.stats_out != nullptr && (c & 1) == 0) {
+            st_s = 0.f;
+            st_q = 0.f;
+            float v0;
+            const int colb = c * 32;
+            if (ep.ln_stats != nullptr) v0 = act_apply(fmaf(__uint_as_float(r[0]), er.ln_a, fmaf(er.ln_b, s_c[colb], s_bias[colb])), ep.act);
+            else v0 = act_apply(__uint_as_float(r[0]) + s_bias[colb], ep.act);
+            if (has_res) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(stage + (ci >> 1) * 4096 + lane * 128 + ((((ci & 1) * 4) ^ (lane & 7)) * 16));
+              v0 += unpack_bf16x2(r0.x).x;
+            }
+            st_k = __bfloat162float(__float2bfloat16_rn(v0));
+          }
+          uint8_t* box = stage + (ci >> 1) * 4096 + lane * 128;          // this thread's row of the box
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int col = c * 32 + g * 8;                               // column inside the tile
+            uint8_t* slot = box + (((((ci & 1) * 4) + g) ^ (lane & 7)) * 16);
+            uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res) rr = *reinterpret_cast<const uint4*>(slot);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);                        // rows past M store zeros
+            if (row_ok && n0 + col < N) o = epi_pack8(ep, er, r + g * 8, s_bias, s_c, col, has_res, rr, st_k, st_s, st_q);
+            *reinterpret_cast<uint4*>(slot) = o;
+          }
+          if (ep.stats_out != nullptr && (c & 1) == 1 && row_ok && n0 + c * 32 < N) {
+            const float mean = st_k + st_s * (1.0f / 64.0f);
+            const float m2 = fmaxf(st_q - st_s * st_s * (1.0f / 64.0f), 0.f);
+            ep.stats_out[(int64_t)row * (N >> 6) + ((n0 + c * 32) >> 6)] = make_float2(mean, m2);
+          }
+          if (ci & 1) {
+            // a 64-column box is complete: generic-proxy writes -> visible to the TMA engine, then one store
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && row0 < M && col0 + (ci >> 1) * 64 < N) {
+              ptx::tma_store_2d(&tmC, stage + (ci >> 1) * 4096, col0 + (ci >> 1) * 64, out_row0);
+              ptx::bulk_commit_group();
+            }
+          }
+        }
+        if (has_res && row0 < M) rphase ^= 1;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       // residual prefetch: issued before the accumulator wait so its latency overlaps the main loop
       uint4 res[CPW][4];
 #pragma unroll
@@ -210,6 +312,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (TMAST && lane == 0) ptx::bulk_wait_group<0>();   // every store of this thread has been performed before the CTA exits
   }
 
   ptx::tc_fence_before();

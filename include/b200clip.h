@@ -233,6 +233,9 @@ int b200_gemm_bf16_device(const void* d_A, const void* d_W, const float* d_bias,
 /* Large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles) by default; 0 forces the
  * single-CTA 128x256 kernel for every shape (A/B measurements, parity between the two kernels). */
 int b200_gemm_set_pair_mode(int on);
+/* CTA-pair kernel only: 1 = results (and the residual operand) travel through shared memory and TMA tensor
+ * stores / loads instead of per-thread 16-byte global stores / loads; 0 = the register path (A/B, parity tests). */
+int b200_gemm_set_tma_store(int on);
 
 /* Stand-alone entries of the two other embed kernels, for their parity tests:
  * LayerNorm (eps 1e-5) over rows of `w` bf16 values; multi-head attention over a fused qkv buffer

@@ -56,3 +56,41 @@ def test_gemm_matches_fp32_reference(M, N, K, act, bias, res):
     # bf16 output: half an ulp = 2^-9 relative; allow 2^-7 relative + 0.02 absolute for the fp32 sums
     assert not torch.isnan(out.float()).any()
     assert bool((err <= ref.abs() * 2 ** -7 + 0.02).all()), "max err %g" % err.max().item()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("M,N,K,act,bias,res", [
+    (20001, 3072, 1024, 1, True, False),   # qkv / fc shape class, ragged M
+    (20001, 1024, 1024, 0, True, True),    # out-proj: residual prefetched by TMA, stored in place of it
+    (19000, 1000, 520, 2, True, True),     # N and K tails: boxes clipped by the tensor maps
+    (40000, 768, 3072, 0, True, True),     # text c_proj shape class
+])
+def test_pair_gemm_tma_store_equals_register_store(M, N, K, act, bias, res):
+    """The CTA-pair kernel's two epilogues (results through shared memory + TMA tensor stores vs per-thread stores)
+    compute the same values: bit-identical outputs, also when the output buffer IS the residual (in-place update of
+    the residual stream, as the model runs it)."""
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    g = torch.Generator(device="cuda").manual_seed(M + 31 * N + 977 * K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    R = torch.randn(M, N, device="cuda", generator=g).bfloat16() if res else None
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    try:
+        for mode in (0, 1):
+            check(lib.b200_gemm_set_tma_store(mode), "set_tma_store")
+            out = R.clone() if res else torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+            check(lib.b200_gemm_bf16_device(A.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None,
+                                            out.data_ptr() if res else None, out.data_ptr(), M, N, K, act, 0, st), "gemm")
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        check(lib.b200_gemm_set_tma_store(0), "set_tma_store")
+    assert not torch.isnan(outs[1].float()).any()
+    assert torch.equal(outs[0], outs[1]), "max diff %g" % (outs[0].float() - outs[1].float()).abs().max().item()
+    ref = _ref(A, W, b, R, act)
+    err = (outs[1].float() - ref).abs()
+    assert bool((err <= ref.abs() * 2 ** -7 + 0.02).all()), "max err %g" % err.max().item()
