@@ -210,7 +210,9 @@ struct SpanGuard {
 static int run_linear(b200_clip* m, const CUtensorMap& tmA, const Linear& l, int M, GemmEpilogue ep, cudaStream_t st,
                       int kind = CLS_GEMM, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr) {
   SpanGuard sg(m, kind, st);
-  const int bn = gemm_pick_bn(M, l.N, m->sms);
+  int bn = gemm_pick_bn(M, l.N, m->sms);
+  // row statistics are written per 64-column slot by ONE thread: the narrow tiles split a slot over two warps
+  if (ep.stats_out != nullptr && bn < 128) bn = 128;
   ep.bias = l.b;
   m->last_launches++;
   const CUtensorMap& tmB = bn == 256 ? l.tm256 : (bn == 64 ? l.tm64 : (bn == 32 ? l.tm32 : l.tm128));   // pair mode: tm128

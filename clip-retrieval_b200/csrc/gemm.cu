@@ -120,7 +120,8 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
              "gemm: output must be 16-byte aligned with ld %% 8 == 0");
   B200_CHECK(ep.residual == nullptr || (ep.res_ld % 8 == 0 && ((uintptr_t)ep.residual & 15) == 0), B200_ERR_INVALID,
              "gemm: residual must be 16-byte aligned with ld %% 8 == 0");
-  B200_CHECK(ep.stats_out == nullptr || N % 64 == 0, B200_ERR_INVALID, "gemm: row statistics need N %% 64 == 0 (N=%d)", N);
+  B200_CHECK(ep.stats_out == nullptr || (N % 64 == 0 && bn >= 128), B200_ERR_INVALID,
+             "gemm: row statistics need N %% 64 == 0 and tiles of at least 128 columns (N=%d, bn=%d)", N, bn);
   B200_CHECK(ep.ln_stats == nullptr || (ep.ln_c != nullptr && ep.ln_w > 0 && ep.ln_w % 64 == 0), B200_ERR_INVALID,
              "gemm: folded LayerNorm needs c and a row width that is a multiple of 64 (ln_w=%d)", ep.ln_w);
   B200_CHECK(ep.ln_stats == nullptr || ep.ln_w <= 64 * LN_MAX_SLOTS, B200_ERR_UNSUPPORTED, "gemm: folded LayerNorm supports rows of at most %d columns", 64 * LN_MAX_SLOTS);
