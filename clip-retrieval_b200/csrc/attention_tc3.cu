@@ -92,8 +92,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
-      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, 5);
-      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 5);
+      // with leftover rows the last tile's softmax group (4 warps) also reads K / V from shared memory
+      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, fma_rows > 0 ? 5 : 1);
+      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, fma_rows > 0 ? 5 : 1);
       for (int i = 0; i < 2; i++) {
         ptx::mbar_init(&s_full[i], 1);
         ptx::mbar_init(&p_full[i], 4);
@@ -140,48 +141,51 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
     if (lane == 0) {
       const uint32_t idesc_s = ptx::umma_idesc_f16(128, keys_main, true);
       const uint32_t idesc_o = ptx::umma_idesc_f16(128, A3_HD, true) | (1u << 16);  // B (= V) is MN-major
-      uint32_t it = 0, tc = 0;
-      bool have_prev = false;
-      uint32_t prev_tc = 0, prev_it = 0;
-      bool prev_last = false, prev_first = false;
-      auto issue_pv = [&](uint32_t ptc, bool first_of_item, bool last_of_item, uint32_t pit) {
-        const int pb = ptc & 1;
-        if (first_of_item) ptx::mbar_wait(v_full, pit & 1);
-        ptx::mbar_wait(&p_full[pb], (ptc >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint8_t* sPg = sP + pb * A3_P_BYTES;
-        for (int ks = 0; ks < keys_main / 16; ks++) {
-          const uint64_t dp = ptx::umma_desc_k_sw128(ptx::smem_u32(sPg + (ks >> 2) * (128 * 128))) + (uint64_t)((ks & 3) * 2);
-          const uint64_t dv = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + ks * 16 * 128));  // 16 keys = 2 swizzle atoms
-          ptx::umma_f16(tmem_base + pb * 256, dp, dv, idesc_o, ks != 0 ? 1u : 0u);
+      // Two cursors over this CTA's tile sequence: the next S = Q K^T and the next O = P V.  Whichever has its inputs
+      // ready is issued (non-blocking mbarrier tests): a fixed order S(t+1) before PV(t) made every P.V wait for the
+      // NEXT head's K load and serialised the two softmax groups (17.8 % of all stall samples on the o_full spin,
+      // profiles/r02d_attn3).  P.V first: it unblocks a softmax group and frees a TMEM buffer.
+      const int my_items = blockIdx.x < items ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const uint32_t total = (uint32_t)my_items * (uint32_t)q_tiles;
+      uint32_t s_tc = 0, s_it = 0, pv_tc = 0, pv_it = 0;
+      int s_mt = 0, pv_mt = 0;
+      while (pv_tc < total) {
+        bool did = false;
+        if (pv_tc < s_tc) {
+          const int pb = pv_tc & 1;
+          if ((pv_mt != 0 || ptx::mbar_try_wait(v_full, pv_it & 1)) && ptx::mbar_try_wait(&p_full[pb], (pv_tc >> 1) & 1)) {
+            ptx::tc_fence_after();
+            const uint8_t* sPg = sP + pb * A3_P_BYTES;
+            for (int ks = 0; ks < keys_main / 16; ks++) {
+              const uint64_t dp = ptx::umma_desc_k_sw128(ptx::smem_u32(sPg + (ks >> 2) * (128 * 128))) + (uint64_t)((ks & 3) * 2);
+              const uint64_t dv = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + ks * 16 * 128));  // 16 keys = 2 swizzle atoms
+              ptx::umma_f16(tmem_base + pb * 256, dp, dv, idesc_o, ks != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&o_full[pb]);
+            if (pv_mt == q_tiles - 1) ptx::umma_commit(v_free);
+            pv_tc++;
+            if (++pv_mt == q_tiles) { pv_mt = 0; pv_it++; }
+            did = true;
+          }
         }
-        ptx::umma_commit(&o_full[pb]);
-        if (last_of_item) ptx::umma_commit(v_free);
-      };
-      for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
-        for (int mt = 0; mt < q_tiles; mt++, tc++) {
-          const int bsel = tc & 1;
-          if (mt == 0) ptx::mbar_wait(k_full, it & 1);
-          ptx::mbar_wait(q_full, tc & 1);
-          ptx::mbar_wait(&buf_free[bsel], ((tc >> 1) & 1) ^ 1);   // O(tc-2) has been read out of this buffer
-          ptx::tc_fence_after();
-          const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
-          const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
+        if (!did && s_tc < total && s_tc < pv_tc + 2) {
+          const int bsel = s_tc & 1;
+          if ((s_mt != 0 || ptx::mbar_try_wait(k_full, s_it & 1)) && ptx::mbar_try_wait(q_full, s_tc & 1) &&
+              ptx::mbar_try_wait(&buf_free[bsel], ((s_tc >> 1) & 1) ^ 1)) {   // O(s_tc - 2) has been read out of this buffer
+            ptx::tc_fence_after();
+            const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
+            const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
 #pragma unroll
-          for (int k = 0; k < A3_HD / 16; k++)
-            ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
-          ptx::umma_commit(q_empty);
-          ptx::umma_commit(&s_full[bsel]);
-          if (mt == q_tiles - 1) ptx::umma_commit(k_free);
-          if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
-          have_prev = true;
-          prev_tc = tc;
-          prev_first = mt == 0;
-          prev_last = mt == q_tiles - 1;
-          prev_it = it;
+            for (int k = 0; k < A3_HD / 16; k++)
+              ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+            ptx::umma_commit(q_empty);
+            ptx::umma_commit(&s_full[bsel]);
+            if (s_mt == q_tiles - 1) ptx::umma_commit(k_free);
+            s_tc++;
+            if (++s_mt == q_tiles) { s_mt = 0; s_it++; }
+          }
         }
       }
-      if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
     }
     __syncwarp();
   } else {
@@ -305,7 +309,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
           }
           // K of this head is no longer needed by this group (the other group never reads it)
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(k_free);
+          if (lane == 0 && fma_rows > 0) ptx::mbar_arrive(k_free);
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
@@ -476,7 +480,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
             }
           }
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(v_free);
+          if (lane == 0 && fma_rows > 0) ptx::mbar_arrive(v_free);
         }
       }
     }

@@ -97,9 +97,9 @@ struct b200_clip {
   std::map<int, TowerGraph> graphs;   // key: image | B << 1 | f16 << 12 | normalize << 13
   void* g_in = nullptr;
   void* g_out = nullptr;
-  bool use_graphs = false;     // B200_GRAPHS=1 enables (default off until verified on hardware this round)
+  bool use_graphs = true;      // B200_GRAPHS=0 disables (A/B, debugging)
   cudaStream_t cap_stream = nullptr;
-  bool fuse_ln = false;        // LayerNorm of every block folded into the qkv / fc GEMMs (B200_FUSE_LN=1; default off until verified)
+  bool fuse_ln = false;        // LayerNorm folded into the qkv / fc GEMMs (B200_FUSE_LN=1): correct, but measured slower than the LN kernel it removes
   int attn_gen = 2;            // 3: attention_tc3.cu (single score pass); 2: attention_tc2.cu (B200_ATTN_GEN; default 2 until verified)
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
   bool attn_v_direct = true;   // P.V reads V from the qkv buffer as an MN-major operand (no V^T copy)

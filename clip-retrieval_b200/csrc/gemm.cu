@@ -70,7 +70,7 @@ void gemm_set_pair_mode(bool on) { g_pair_enabled = on; }
 // pair kernel: results through shared memory + TMA stores (B200_GEMM_TMA_STORE=0/1; default in gemm_tma_store_default)
 static bool gemm_tma_store_default() {
   const char* e = getenv("B200_GEMM_TMA_STORE");
-  return e ? atoi(e) != 0 : false;   // opt-in until verified on hardware
+  return e ? atoi(e) != 0 : true;    // verified on B200: bit-identical to the register path, +20 % on the K=1024 shapes (profiles/r02d)
 }
 static bool g_tma_store = gemm_tma_store_default();
 void gemm_set_tma_store(bool on) { g_tma_store = on; }

@@ -212,12 +212,16 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after();
         if (has_res && row0 < M) ptx::mbar_wait(&rbar[warp], rphase);
+        // the accumulator chunk c+1 is in flight (tcgen05.ld) while chunk c is finished and staged
+        uint32_t rbuf[2][32];
+        const uint32_t tacc = tmem_base + acc * G2_BN + half * CPW * 32 + ((uint32_t)(q * 32) << 16);
+        ptx::tmem_ld_32x32b_x32(tacc, rbuf[0]);
 #pragma unroll
         for (int ci = 0; ci < CPW; ci++) {
           const int c = half * CPW + ci;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + acc * G2_BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+          uint32_t(&r)[32] = rbuf[ci & 1];
           ptx::tmem_ld_wait();
+          if (ci + 1 < CPW) ptx::tmem_ld_32x32b_x32(tacc + (ci + 1) * 32, rbuf[(ci + 1) & 1]);
           if (ci == CPW - 1) {
             ptx::tc_fence_before();
             __syncwarp();

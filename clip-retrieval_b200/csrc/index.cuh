@@ -52,7 +52,7 @@ struct b200_index {
   struct SearchGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int kernels = 0; uint64_t epoch = 0; };
   std::map<uint64_t, SearchGraph> graphs;
   uint64_t graph_epoch = 1;
-  bool use_graphs = false;    // B200_GRAPHS=1 enables (default off until verified on hardware this round)
+  bool use_graphs = true;     // B200_GRAPHS=0 disables
   cudaStream_t cap_stream = nullptr;
   bool capturing = false;     // timing events are recorded as external event nodes while a graph is captured
   float* g_q = nullptr; float* g_D = nullptr; int64_t* g_I = nullptr; float* g_R = nullptr;

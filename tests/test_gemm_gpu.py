@@ -88,7 +88,7 @@ def test_pair_gemm_tma_store_equals_register_store(M, N, K, act, bias, res):
             torch.cuda.synchronize()
             outs.append(out)
     finally:
-        check(lib.b200_gemm_set_tma_store(0), "set_tma_store")
+        check(lib.b200_gemm_set_tma_store(1), "set_tma_store")    # the default
     assert not torch.isnan(outs[1].float()).any()
     assert torch.equal(outs[0], outs[1]), "max diff %g" % (outs[0].float() - outs[1].float()).abs().max().item()
     ref = _ref(A, W, b, R, act)
