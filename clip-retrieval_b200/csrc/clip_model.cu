@@ -431,6 +431,9 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
   m->device = device;
   m->sms = sm_count(device);
   if (const char* g = getenv("B200_ATTN_GEN")) m->attn_gen = atoi(g);
+  // LayerNorm folded into the qkv / fc GEMMs stays opt-in: at throughput batch sizes the epilogue is the pair GEMM's
+  // bottleneck and the fold costs more than the LN kernel it removes (profiles/r02d_model_ab.txt); at serving batch
+  // sizes the row statistics need >= 128-column tiles, which undoes the narrow-tile weight streaming.
   if (const char* g = getenv("B200_FUSE_LN")) m->fuse_ln = atoi(g) != 0;
   if (const char* g = getenv("B200_GRAPHS")) m->use_graphs = atoi(g) != 0;
   m->grid = cfg->image_size / cfg->patch;
