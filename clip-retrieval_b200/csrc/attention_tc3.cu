@@ -25,6 +25,7 @@
 #include "embed_kernels.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -54,7 +55,7 @@ __device__ __forceinline__ void a3_unpack8(const uint4& u, float* f) {
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat16* __restrict__ qkv,
                      __nv_bfloat16* __restrict__ out, const float* __restrict__ kmax_head, int B, int T, int heads, int w,
-                     float scale_log2e, int causal) {
+                     float scale_log2e, int causal, int onepass) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -67,9 +68,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;
-  uint64_t* k_free = bars + 3;    // MMA commit (last S of the head) + the 4 warps of the last tile's softmax group
+  uint64_t* k_free = bars + 3;    // MMA commit after the last S of the head
   uint64_t* v_full = bars + 4;
-  uint64_t* v_free = bars + 5;    // MMA commit (last P.V of the head) + the 4 warps of the last tile's softmax group
+  uint64_t* v_free = bars + 5;    // MMA commit after the last P.V of the head
   uint64_t* s_full = bars + 6;    // [2]
   uint64_t* p_full = bars + 8;    // [2]
   uint64_t* o_full = bars + 10;   // [2]
@@ -92,9 +93,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
-      // with leftover rows the last tile's softmax group (4 warps) also reads K / V from shared memory
-      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, fma_rows > 0 ? 5 : 1);
-      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, fma_rows > 0 ? 5 : 1);
+      ptx::mbar_init(k_full, 1); ptx::mbar_init(k_free, 1);
+      ptx::mbar_init(v_full, 1); ptx::mbar_init(v_free, 1);
       for (int i = 0; i < 2; i++) {
         ptx::mbar_init(&s_full[i], 1);
         ptx::mbar_init(&p_full[i], 4);
@@ -212,7 +212,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
 #pragma unroll
         for (int e = 0; e < 8; e++) se[e] = -INFINITY;
         float qn2 = 0.f;
-        {
+        if (onepass || extra > 0) {
           float qf[A3_HD];
           const int qr = qrow < T ? qrow : T - 1;
           const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + qr) * 3 * w + (size_t)h * A3_HD);
@@ -235,14 +235,15 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               if (ee == e) se[ee] = (256 + e <= kmax) ? acc : -INFINITY;
           }
         }
-        const float kn = __ldg(kmax_head + item);
-        float mb = sqrtf(qn2) * 1.0001f * kn * scale_log2e;      // >= every score of this row, in log2 units
+        float mb = 0.f;
+        if (onepass) mb = sqrtf(qn2) * 1.0001f * __ldg(kmax_head + item) * scale_log2e;   // >= every score of this row (log2 units)
         // ---- leftover query rows of this head (T mod 128 <= 4): scores and probabilities now, while K is resident ----
         const bool last_tile = mt == q_tiles - 1;
         float tail_l[A3_TAIL_MAX];
         if (last_tile) {
           if (fma_rows > 0) {
-            ptx::mbar_wait(k_full, it & 1);
+            // K and V rows of the head come from the qkv buffer (L2: the TMA boxes of this head were just read from
+            // there), not from the shared-memory tiles: nothing here holds the tiles back from the next head
             for (int fr = 0; fr < fma_rows; fr++) {
               const int trow = n_full * 128 + fr;
               const int tkmax = causal ? trow : T - 1;
@@ -250,35 +251,24 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + trow) * 3 * w + (size_t)h * A3_HD);
 #pragma unroll
               for (int c = 0; c < 8; c++) a3_unpack8(__ldg(qp + c), qf + c * 8);
-              // thread r: keys r, r + 128 from shared memory; key 256 + r (r < extra) from the qkv buffer
+              // thread r: keys r, r + 128, r + 256
               float sc[3];
 #pragma unroll
               for (int u = 0; u < 3; u++) {
-                const int j = u < 2 ? r + u * 128 : 256 + r;
+                const int j = r + u * 128;
                 float acc = -INFINITY;
-                if (j <= tkmax && (u < 2 ? j < keys_main : r < extra)) {
+                if (j <= tkmax) {
                   acc = 0.f;
-                  if (u < 2) {
-                    const uint8_t* row = sK + (j >> 7) * (128 * 128) + (j & 127) * 128;
+                  const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                      float f[8];
-                      a3_unpack8(*reinterpret_cast<const uint4*>(row + ((c ^ (j & 7)) * 16)), f);
+                  for (int c = 0; c < 8; c++) {
+                    float f[8];
+                    a3_unpack8(__ldg(kp + c), f);
 #pragma unroll
-                      for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
-                    }
-                  } else {
-                    const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + j) * 3 * w + w + (size_t)h * A3_HD);
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                      float f[8];
-                      a3_unpack8(__ldg(kp + c), f);
-#pragma unroll
-                      for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
-                    }
+                    for (int e = 0; e < 8; e++) acc = fmaf(qf[c * 8 + e], f[e], acc);
                   }
                 }
-                sc[u] = acc;
+              sc[u] = acc;
               }
               // exact two-pass softmax over the 128 threads of the group
               float mx = fmaxf(fmaxf(sc[0], sc[1]), sc[2]);
@@ -295,7 +285,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(sc[u], scale_log2e, -mbt)));
                 pv = sc[u] == -INFINITY ? 0.f : pv;
                 ls += pv;
-                const int j = u < 2 ? r + u * 128 : 256 + r;
+                const int j = r + u * 128;
                 // P is rounded to bf16 before it multiplies V, as on the tensor-core rows; the row sum keeps fp32
                 if (j < 264) sTp[fr * 264 + j] = __bfloat162float(__float2bfloat16_rn(pv));
               }
@@ -307,22 +297,45 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               a3_group_sync(grp);   // sTr is reused by the next row
             }
           }
-          // K of this head is no longer needed by this group (the other group never reads it)
-          __syncwarp();
-          if (lane == 0 && fma_rows > 0) ptx::mbar_arrive(k_free);
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
 
-        float l, tmax;
+        float l = 0.f, tmax = -INFINITY;
         float pe[8];
-        // one pass: exponentials against the bound, row sum, true maximum, P -> swizzled K-major tile of this group
-        auto pass = [&](const float mbv) {
+        if (!onepass) {
+          // two-pass mode: the exact row maximum first (one more read of the scores out of TMEM)
+          float m = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
+#pragma unroll 1
+          for (int c = 0; c < chunks; c++) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int lim = kmax - c * 32;
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
+              m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
+              m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
+              m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
+            }
+            m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          }
+          mb = m * scale_log2e;
+        }
+        // exponentials against mb (the bound, or the exact maximum), row sum, true maximum, P -> swizzled K-major tile.
+        // One-pass mode: if the bound sits too far above the true maximum of some row of this warp, the pass is
+        // repeated with exact maxima (S is still in TMEM, P is simply rewritten).
+        for (int attempt = 0; attempt < 2; attempt++) {
           float l0 = 0.f, l1 = 0.f, t0 = -INFINITY, t1 = -INFINITY;
-          uint32_t va[32], vb[32];
-          ptx::tmem_ld_32x32b_x32(tbase, va);
-          ptx::tmem_ld_wait();
-          auto chunk_fn = [&](const uint32_t (&v)[32], const int c) {
+#pragma unroll 1
+          for (int c = 0; c < chunks; c++) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+            ptx::tmem_ld_wait();
             const int lim = kmax - c * 32;
             uint32_t pk[16];
             if (lim >= 31) {
@@ -330,8 +343,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               for (int j = 0; j < 32; j += 2) {
                 const float s0 = __uint_as_float(v[j]), s1 = __uint_as_float(v[j + 1]);
                 float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mbv)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mbv)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mb)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mb)));
                 t0 = fmaxf(t0, s0);
                 t1 = fmaxf(t1, s1);
                 l0 += p0;
@@ -344,8 +357,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
                 const float s0 = j <= lim ? __uint_as_float(v[j]) : -INFINITY;
                 const float s1 = j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY;
                 float p0, p1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mbv)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mbv)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s0, scale_log2e, -mb)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s1, scale_log2e, -mb)));
                 p0 = j <= lim ? p0 : 0.f;
                 p1 = j + 1 <= lim ? p1 : 0.f;
                 t0 = fmaxf(t0, s0);
@@ -361,36 +374,21 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
               *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
             }
-          };
-#pragma unroll 1
-          for (int c = 0; c < chunks; c += 2) {
-            if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);   // in flight while chunk c is processed
-            chunk_fn(va, c);
-            ptx::tmem_ld_wait();
-            if (c + 1 < chunks) {
-              if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
-              chunk_fn(vb, c + 1);
-              ptx::tmem_ld_wait();
-            }
           }
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             float p;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(se[e], scale_log2e, -mbv)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(se[e], scale_log2e, -mb)));
             pe[e] = se[e] == -INFINITY ? 0.f : p;
             l0 += pe[e];
             t0 = fmaxf(t0, se[e]);
           }
           l = l0 + l1;
           tmax = fmaxf(t0, t1);
-        };
-        pass(mb);
-        // the bound is safe against overflow by construction; if it sits too far above the true maximum of some
-        // row of this warp, redo the pass with exact maxima (S is still in TMEM, P is simply rewritten)
-        const float exact = tmax * scale_log2e;
-        if (__any_sync(0xffffffffu, (mb - exact > A3_MAX_SLACK) && tmax != -INFINITY)) {
+          if (!onepass) break;
+          const float exact = tmax * scale_log2e;
+          if (!__any_sync(0xffffffffu, (mb - exact > A3_MAX_SLACK) && tmax != -INFINITY)) break;
           mb = tmax == -INFINITY ? mb : exact;
-          pass(mb);
         }
         ptx::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
         ptx::tc_fence_before();
@@ -439,29 +437,26 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
         // ---- leftover query rows: O = P V on the FMA pipe, V still resident; then V is released ----
         if (last_tile) {
           if (fma_rows > 0) {
-            ptx::mbar_wait(v_full, it & 1);
             const int dp = lane;                              // dims 2 dp, 2 dp + 1
-            const int chunk = dp >> 2, within = (dp & 3) * 4;
             for (int fr = 0; fr < fma_rows; fr++) {
               const int trow = n_full * 128 + fr;
               const int tkmax = causal ? trow : T - 1;
               const float* pr = sTp + fr * 264;
               float a0 = 0.f, a1 = 0.f;
-              // warp q4 of the group: keys [64 q4, 64 q4 + 64); warp 3 also the keys >= 256
-              const int j0 = q4 * 64, j1 = min(min(j0 + 64, keys_main), tkmax + 1);
-#pragma unroll 4
+              // warp q4 of the group: keys 64 q4 .. 64 q4 + 63; warp 3 also the keys >= 256 (V rows from L2, 128 B per warp)
+              const uint32_t* vbase = reinterpret_cast<const uint32_t*>(qkv + (size_t)b * T * 3 * w + 2 * w + (size_t)h * A3_HD) + dp;
+              const size_t vstride = (size_t)3 * w / 2;       // row pitch in 32-bit words
+              const int j0 = q4 * 64, j1 = min(j0 + 64, tkmax + 1);
+#pragma unroll 8
               for (int j = j0; j < j1; j++) {
-                const uint8_t* row = sV + (j >> 7) * (128 * 128) + (j & 127) * 128;
-                const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + ((chunk ^ (j & 7)) * 16) + within));
+                const float2 vv = unpack_bf16x2(__ldg(vbase + (size_t)j * vstride));
                 const float pj = pr[j];
                 a0 = fmaf(pj, vv.x, a0);
                 a1 = fmaf(pj, vv.y, a1);
               }
               if (q4 == 3) {
-                for (int e = 0; e < extra; e++) {
-                  const int j = 256 + e;
-                  if (j > tkmax) break;
-                  const float2 vv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(qkv + ((size_t)b * T + j) * 3 * w + 2 * w + (size_t)h * A3_HD) + dp));
+                for (int j = 256; j <= tkmax; j++) {
+                  const float2 vv = unpack_bf16x2(__ldg(vbase + (size_t)j * vstride));
                   const float pj = pr[j];
                   a0 = fmaf(pj, vv.x, a0);
                   a1 = fmaf(pj, vv.y, a1);
@@ -479,8 +474,6 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               a3_group_sync(grp);   // sTo is reused by the next row
             }
           }
-          __syncwarp();
-          if (lane == 0 && fma_rows > 0) ptx::mbar_arrive(v_free);
         }
       }
     }
@@ -522,8 +515,14 @@ bool attention_tc3_supported(int T, int heads, int w) {
   return heads > 0 && w % heads == 0 && w / heads == A3_HD && T >= 1 && T <= A3_MAXT;
 }
 
+static int attn3_onepass_default() {
+  const char* e = getenv("B200_ATTN_ONEPASS");
+  return e ? atoi(e) : 0;
+}
+
 int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* kmax_scratch, int B, int T,
                   int heads, int w, int causal, int sms, cudaStream_t st) {
+  static const int onepass = attn3_onepass_default();
   B200_CHECK(kmax_scratch != nullptr, B200_ERR_INVALID, "attention_tc3: needs a [B * heads] fp32 scratch");
   B200_CHECK(attention_tc3_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc3: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
@@ -538,9 +537,11 @@ int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat1
   const float scale_log2e = (1.0f / sqrtf((float)A3_HD)) * 1.4426950408889634f;
   const int items = B * heads;
   const int grid = items < sms ? items : sms;
-  attn_kmax_kernel<<<(items + 7) / 8, 256, 0, st>>>(qkv, B, T, heads, w, kmax_scratch);
-  B200_LAUNCH_OK();
-  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, kmax_scratch, B, T, heads, w, scale_log2e, causal);
+  if (onepass) {
+    attn_kmax_kernel<<<(items + 7) / 8, 256, 0, st>>>(qkv, B, T, heads, w, kmax_scratch);
+    B200_LAUNCH_OK();
+  }
+  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, kmax_scratch, B, T, heads, w, scale_log2e, causal, onepass);
   B200_LAUNCH_OK();
   return B200_OK;
 }
