@@ -39,10 +39,10 @@ def l14():
 
 
 @pytest.mark.timeout(900)
-def test_vit_l14_image_batch64_pair_gemm_matches_oracle(l14):
-    """B=64: 65 row blocks x 4 column blocks = 260 pair tiles even for out-proj (N=1024), 256 for the patch GEMM."""
+def test_vit_l14_image_batch48_pair_gemm_matches_oracle(l14):
+    """B=48: 49 row blocks x 4 column blocks = 196 pair tiles even for out-proj (N=1024), 192 for the patch GEMM."""
     model, cfg, sd = l14
-    B = 64
+    B = 48
     assert _pair_tiles(B * 257, 1024) >= 148 and _pair_tiles(B * 256, 1024) >= 148
     px = clip_ref.synth_images(B, cfg, seed=11)
     got = model.embed_image_device(px.cuda()).cpu().numpy()
@@ -53,10 +53,10 @@ def test_vit_l14_image_batch64_pair_gemm_matches_oracle(l14):
 
 
 @pytest.mark.timeout(900)
-def test_vit_l14_text_batch256_pair_gemm_matches_oracle(l14):
-    """B=256: 77 row blocks x 3 column blocks = 231 pair tiles for out-proj / c_proj (N=768)."""
+def test_vit_l14_text_batch192_pair_gemm_matches_oracle(l14):
+    """B=192: 58 row blocks x 3 column blocks = 174 pair tiles for out-proj / c_proj (N=768)."""
     model, cfg, sd = l14
-    B = 256
+    B = 192
     assert _pair_tiles(B * 77, 768) >= 148
     tk = clip_ref.synth_tokens(B, cfg, seed=12)
     got = model.embed_text_device(tk.cuda()).cpu().numpy()
@@ -101,7 +101,7 @@ def test_pair_and_single_cta_gemm_agree_inside_the_model_at_batch_1024():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("B", [600, 257, 64])
+@pytest.mark.parametrize("B", [600, 64])
 def test_pipelined_host_entry_matches_device_entry(B):
     """encode_host with max_batch >= 256 splits images into four sub-batch slots (H2D on the copy stream
     overlapping compute) and loops over chunks of max_batch; B = 600 = 256 + 256 + 88 leaves a ragged last
