@@ -153,7 +153,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
         bool did = false;
         if (pv_tc < s_tc) {
           const int pb = pv_tc & 1;
-          if ((pv_mt != 0 || ptx::mbar_try_wait(v_full, pv_it & 1)) && ptx::mbar_try_wait(&p_full[pb], (pv_tc >> 1) & 1)) {
+          if ((pv_mt != 0 || ptx::mbar_test_wait(v_full, pv_it & 1)) && ptx::mbar_test_wait(&p_full[pb], (pv_tc >> 1) & 1)) {
             ptx::tc_fence_after();
             const uint8_t* sPg = sP + pb * A3_P_BYTES;
             for (int ks = 0; ks < keys_main / 16; ks++) {
@@ -170,8 +170,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
         }
         if (!did && s_tc < total && s_tc < pv_tc + 2) {
           const int bsel = s_tc & 1;
-          if ((s_mt != 0 || ptx::mbar_try_wait(k_full, s_it & 1)) && ptx::mbar_try_wait(q_full, s_tc & 1) &&
-              ptx::mbar_try_wait(&buf_free[bsel], ((s_tc >> 1) & 1) ^ 1)) {   // O(s_tc - 2) has been read out of this buffer
+          if ((s_mt != 0 || ptx::mbar_test_wait(k_full, s_it & 1)) && ptx::mbar_test_wait(q_full, s_tc & 1) &&
+              ptx::mbar_test_wait(&buf_free[bsel], ((s_tc >> 1) & 1) ^ 1)) {   // O(s_tc - 2) has been read out of this buffer
             ptx::tc_fence_after();
             const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
             const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
@@ -446,13 +446,21 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
               // warp q4 of the group: keys 64 q4 .. 64 q4 + 63; warp 3 also the keys >= 256 (V rows from L2, 128 B per warp)
               const uint32_t* vbase = reinterpret_cast<const uint32_t*>(qkv + (size_t)b * T * 3 * w + 2 * w + (size_t)h * A3_HD) + dp;
               const size_t vstride = (size_t)3 * w / 2;       // row pitch in 32-bit words
-              const int j0 = q4 * 64, j1 = min(j0 + 64, tkmax + 1);
-#pragma unroll 8
-              for (int j = j0; j < j1; j++) {
-                const float2 vv = unpack_bf16x2(__ldg(vbase + (size_t)j * vstride));
-                const float pj = pr[j];
-                a0 = fmaf(pj, vv.x, a0);
-                a1 = fmaf(pj, vv.y, a1);
+              const int j0 = q4 * 64;
+#pragma unroll 1
+              for (int half64 = 0; half64 < 2; half64++) {
+                const int jb = j0 + half64 * 32;
+                uint32_t vr[32];
+#pragma unroll
+                for (int jj = 0; jj < 32; jj++)   // every load issued before the first is used: one L2 latency, not 32
+                  vr[jj] = (jb + jj <= tkmax) ? __ldg(vbase + (size_t)(jb + jj) * vstride) : 0u;
+#pragma unroll
+                for (int jj = 0; jj < 32; jj++) {
+                  const float2 vv = unpack_bf16x2(vr[jj]);
+                  const float pj = (jb + jj <= tkmax) ? pr[jb + jj] : 0.f;
+                  a0 = fmaf(pj, vv.x, a0);
+                  a1 = fmaf(pj, vv.y, a1);
+                }
               }
               if (q4 == 3) {
                 for (int j = 256; j <= tkmax; j++) {
