@@ -183,8 +183,12 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
             if (s_mt == q_tiles - 1) ptx::umma_commit(k_free);
             s_tc++;
             if (++s_mt == q_tiles) { s_mt = 0; s_it++; }
+            did = true;
           }
         }
+        // nothing ready: yield the issue slots of this sub-partition to the two softmax warps that share it (a
+        // spinning issuer executed 7 M instructions per SM and slowed exactly the warps every tile waits for)
+        if (!did) __nanosleep(64);
       }
     }
     __syncwarp();
