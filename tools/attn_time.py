@@ -9,7 +9,10 @@ from clip_retrieval_b200._lib import lib, check
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 st = torch.cuda.current_stream().cuda_stream
-for name, T, heads, causal in (("vision", 257, 16, 0), ("text", 77, 12, 1)):
+shapes = [("vision", 257, 16, 0), ("text", 77, 12, 1)]
+if len(sys.argv) > 2:   # extra token counts for the vision shape, e.g. 256 (no leftover row), 129, 260
+    shapes = [("vision T=%s" % t, int(t), 16, 0) for t in sys.argv[2:]]
+for name, T, heads, causal in shapes:
     w = heads * 64
     qkv = torch.randn(B * T, 3 * w, device="cuda").bfloat16()
     out = torch.empty(B * T, w, device="cuda", dtype=torch.bfloat16)
