@@ -178,6 +178,23 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         if ((int)(tc & 1) != grp) continue;
         const uint32_t n = tc >> 1;
         const int qrow = mt * 128 + r;
+        if (mt * 128 + q4 * 32 >= T) {
+          // every row of this warp lies past the sequence (T = 257: three of the four warps of the third tile):
+          // no scores to read, no exponentials, nothing to store — the P rows it would have written only feed
+          // output rows nobody keeps.  It still takes part in the hand-shakes of the tile.
+          ptx::mbar_wait(&s_full[grp], n & 1);
+          ptx::tc_fence_after();
+          ptx::fence_proxy_async();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
+          ptx::mbar_wait(&o_full[grp], n & 1);
+          ptx::tc_fence_after();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&buf_free[grp]);
+          continue;
+        }
         const int kmax = causal ? (qrow < T ? qrow : T - 1) : T - 1;   // last visible key
         // scores of the extra keys (>= 256) on the FMA pipe: q row from global (L2), k rows from smem
         float se[8];
