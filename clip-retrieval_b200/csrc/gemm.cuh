@@ -116,7 +116,10 @@ __device__ __forceinline__ EpiRow epi_row(const GemmEpilogue& ep, int row, int n
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  // ring depth: the narrow tiles are latency-bound (a CTA's k-loop advances one k-block per TMA round trip divided
+  // by the stages in flight: 278 ns per k-block with 6 stages at BN = 32, profiles/r02b_serve_launches.csv), and
+  // their stages are small — so they get the deepest rings that fit
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
