@@ -77,7 +77,7 @@ struct b200_clip {
   __nv_bfloat16* tok_emb = nullptr;  // [vocab, w]
   float* tpos = nullptr;             // [ctx, w]
   int* pool_idx = nullptr;
-  float* feat = nullptr;             // raw projected features fp32 [min(max_batch, 128), D] (small-batch pool/projection split)
+  float* feat = nullptr;             // raw projected features fp32 [max_batch, D] (pool/projection split over D / 64 blocks)
   // staging for the host entry points
   void* stage_in = nullptr;
   void* stage_out = nullptr;
@@ -457,7 +457,7 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
     B200_TRY(dev_alloc(m, &m->tok_emb, (size_t)cfg->vocab_size * cfg->text.width));
     B200_TRY(dev_alloc(m, &m->tpos, (size_t)cfg->context_length * cfg->text.width));
     B200_TRY(dev_alloc(m, &m->pool_idx, (size_t)cfg->max_batch));
-    B200_TRY(dev_alloc(m, &m->feat, (size_t)std::min(cfg->max_batch, 128) * cfg->embed_dim));
+    B200_TRY(dev_alloc(m, &m->feat, (size_t)cfg->max_batch * cfg->embed_dim));
     const size_t in_bytes = std::max((size_t)cfg->max_batch * 3 * cfg->image_size * cfg->image_size * 4,
                                      (size_t)cfg->max_batch * cfg->context_length * 8);
     B200_CUDA(cudaMalloc(&m->stage_in, in_bytes));

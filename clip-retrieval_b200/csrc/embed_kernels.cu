@@ -306,9 +306,9 @@ pool_proj_kernel(const __nv_bfloat16* __restrict__ x, int T, int w, const int* _
     else reinterpret_cast<float*>(out)[(size_t)b * D + j] = v;
   }
 }
-// Small batches (the serving shape, clip_back.py:226-246: batch 1): one block per sample leaves the projection to a
-// single SM with a w-long dependent loop per thread (0.76 ms at w = D = 768).  Here a block owns 64 output columns
-// of one sample: the pooled row is normalised redundantly per block (w values), the projection is split over
+// One block per sample leaves the projection to a w-long dependent loop per thread: 0.76 ms at batch 1 (a single SM,
+// clip_back.py:226-246's shape) and still 0.72 ms per call at batch 1024 (profiles/r02n_launch_shares.txt).  Here a
+// block owns 64 output columns of one sample: the pooled row is normalised redundantly per block (w values), the projection is split over
 // 64 columns x 4 quarters of the reduction dimension, raw features go to `feat` and a second tiny kernel normalises.
 __global__ void __launch_bounds__(256)
 pool_proj_split_kernel(const __nv_bfloat16* __restrict__ x, int T, int w, const int* __restrict__ pool_idx,
@@ -376,7 +376,7 @@ int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx,
                       const __nv_bfloat16* proj, int D, void* out, int out_f16, int normalize, int B, cudaStream_t st,
                       float* feat_scratch) {
   if (B == 0) return B200_OK;
-  if (feat_scratch != nullptr && B <= 128) {
+  if (feat_scratch != nullptr) {
     const size_t smem2 = (size_t)(w + 256) * sizeof(float);
     B200_CHECK(smem2 <= 48 * 1024, B200_ERR_UNSUPPORTED, "pool_proj: width too large");
     pool_proj_split_kernel<<<dim3((D + 63) / 64, B), 256, smem2, st>>>(x, T, w, pool_idx, gamma, beta, proj, D, feat_scratch);

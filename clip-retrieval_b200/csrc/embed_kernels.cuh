@@ -39,7 +39,7 @@ int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat1
 // -> fp16 or fp32.  pool_idx == nullptr pools token 0 (vision); else row pool_idx[b] (text EOT).
 int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx, const float* gamma, const float* beta,
                       const __nv_bfloat16* proj, int D, void* out, int out_f16, int normalize, int B, cudaStream_t st,
-                      float* feat_scratch = nullptr);   // fp32 [B, D]: batches <= 128 split the projection over D / 64 blocks
+                      float* feat_scratch = nullptr);   // fp32 [B, D]: when given, the projection is split over D / 64 blocks per sample
 // argmax(tokens, dim=-1) (first maximum) -> pool_idx[b]
 int token_argmax(const int64_t* tokens, int* pool_idx, int B, int T, cudaStream_t st);
 
