@@ -25,6 +25,7 @@
 #include "embed_kernels.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "topk.cuh"
 #include <cstdlib>
 
 namespace b200 {
@@ -55,7 +56,7 @@ __device__ __forceinline__ void a3_unpack8(const uint4& u, float* f) {
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat16* __restrict__ qkv,
                      __nv_bfloat16* __restrict__ out, const float* __restrict__ kmax_head, int B, int T, int heads, int w,
-                     float scale_log2e, int causal, int onepass) {
+                     float scale_log2e, int causal, int onepass, int tail_external) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -86,7 +87,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tm3, const __nv_bfloat1
   const int n_full = T / 128, rem = T - n_full * 128;
   const bool tail_rows = rem > 0 && rem <= A3_TAIL_MAX && n_full >= 1;
   const int q_tiles = tail_rows ? n_full : (T + 127) / 128;
-  const int fma_rows = tail_rows ? rem : 0;
+  const int fma_rows = (tail_rows && !tail_external) ? rem : 0;   // leftover rows done by attention_tail_kernel otherwise
   const int items = B * heads;
 
   if (warp == 8 && lane == 0) ptx::prefetch_tensormap(&tm3);
@@ -523,6 +524,83 @@ attn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int heads,
   if (lane == 0) kmax_head[item] = sqrtf(kn2) * 1.0001f + 1e-30f;
 }
 
+// The leftover query rows (T mod 128 <= 4 rows per head; ONE for T = 257) as their own small kernel: one warp per
+// (sample, head, row), K and V of the head straight from the qkv buffer.  Inside the tensor-core kernel these rows sat
+// on one softmax group's critical path (+0.76 ms per ViT-L/14 layer, more than the padded third tile they replace,
+// profiles/r02g_attention_T_sweep.txt); here they run on a second stream next to it — the big kernel leaves the SMs'
+// FMA pipes, registers and most of the DRAM bandwidth idle (ncu: issue 42 %, DRAM 21 %).
+// Scores: lane = dimension pair, 32 keys at a time, one transposing reduction per 32 keys (lane i ends up with key
+// base + i).  P.V: lane = dimension pair again, p_j broadcast by shuffle.  All loads are 128-byte rows.
+__global__ void __launch_bounds__(128)
+attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int T, int heads, int w,
+                      float scale_log2e, int causal, int row0, int nrows) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= B * heads * nrows) return;
+  const int fr = wid % nrows, item = wid / nrows;
+  const int b = item / heads, h = item - b * heads;
+  const int trow = row0 + fr;
+  const int tkmax = causal ? trow : T - 1;
+  const size_t pitch = (size_t)3 * w / 2;                                  // row pitch in 32-bit words
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (size_t)b * T * 3 * w + (size_t)h * A3_HD) + lane;
+  const float2 ql = unpack_bf16x2(__ldg(base + (size_t)trow * pitch));    // this lane's two dimensions of q
+  const uint32_t* kb = base + w / 2;
+  const uint32_t* vb = base + w;
+  constexpr int NB = (A3_MAXT + 31) / 32;                                  // key blocks of 32: 9
+  float s[NB];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int blk = 0; blk < NB; blk++) {
+    s[blk] = -INFINITY;
+    if (blk * 32 <= tkmax) {
+      float part[32];
+      uint32_t kr[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) kr[i] = (blk * 32 + i <= tkmax) ? __ldg(kb + (size_t)(blk * 32 + i) * pitch) : 0u;
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float2 kk = unpack_bf16x2(kr[i]);
+        part[i] = fmaf(ql.x, kk.x, ql.y * kk.y);
+      }
+      warp_transpose_reduce<32>(part, lane);                               // lane i: score of key blk * 32 + i
+      s[blk] = (blk * 32 + lane <= tkmax) ? part[0] : -INFINITY;
+      mx = fmaxf(mx, s[blk]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float mb = mx * scale_log2e;
+  float l = 0.f;
+#pragma unroll
+  for (int blk = 0; blk < NB; blk++) {
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[blk], scale_log2e, -mb)));
+    p = s[blk] == -INFINITY ? 0.f : p;
+    l += p;
+    s[blk] = __bfloat162float(__float2bfloat16_rn(p));   // P is rounded to bf16 before it multiplies V, as on the tensor-core rows
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int blk = 0; blk < NB; blk++) {
+    if (blk * 32 <= tkmax) {
+      uint32_t vr[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) vr[i] = (blk * 32 + i <= tkmax) ? __ldg(vb + (size_t)(blk * 32 + i) * pitch) : 0u;
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float pj = __shfl_sync(0xffffffffu, s[blk], i);
+        const float2 vv = unpack_bf16x2(vr[i]);
+        o0 = fmaf(pj, vv.x, o0);
+        o1 = fmaf(pj, vv.y, o1);
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + trow) * w + (size_t)h * A3_HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
 bool attention_tc3_supported(int T, int heads, int w) {
   return heads > 0 && w % heads == 0 && w / heads == A3_HD && T >= 1 && T <= A3_MAXT;
 }
@@ -533,8 +611,10 @@ static int attn3_onepass_default() {
 }
 
 int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* kmax_scratch, int B, int T,
-                  int heads, int w, int causal, int sms, cudaStream_t st) {
+                  int heads, int w, int causal, int sms, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork,
+                  cudaEvent_t ev_join) {
   static const int onepass = attn3_onepass_default();
+  static const int tail_inside = getenv("B200_ATTN_TAIL_INSIDE") != nullptr;   // A/B: leftover rows inside the big kernel
   B200_CHECK(kmax_scratch != nullptr, B200_ERR_INVALID, "attention_tc3: needs a [B * heads] fp32 scratch");
   B200_CHECK(attention_tc3_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc3: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
@@ -553,8 +633,25 @@ int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat1
     attn_kmax_kernel<<<(items + 7) / 8, 256, 0, st>>>(qkv, B, T, heads, w, kmax_scratch);
     B200_LAUNCH_OK();
   }
-  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, kmax_scratch, B, T, heads, w, scale_log2e, causal, onepass);
+  const int n_full = T / 128, rem = T - n_full * 128;
+  const bool tail_rows = rem > 0 && rem <= A3_TAIL_MAX && n_full >= 1;
+  const bool external = tail_rows && !tail_inside;
+  if (external) {
+    // leftover rows next to the tensor-core kernel: fork to the side stream (when the caller has one), join after
+    const unsigned nw = (unsigned)((size_t)items * rem);
+    cudaStream_t ts = (side != nullptr && ev_fork != nullptr && ev_join != nullptr) ? side : st;
+    if (ts != st) {
+      B200_CUDA(cudaEventRecord(ev_fork, st));
+      B200_CUDA(cudaStreamWaitEvent(ts, ev_fork, 0));
+    }
+    attention_tail_kernel<<<(nw + 3) / 4, 128, 0, ts>>>(qkv, out, B, T, heads, w, scale_log2e, causal, n_full * 128, rem);
+    B200_LAUNCH_OK();
+    if (ts != st) B200_CUDA(cudaEventRecord(ev_join, ts));
+  }
+  attention_tc3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tm3, qkv, out, kmax_scratch, B, T, heads, w, scale_log2e, causal, onepass,
+                                                          external ? 1 : 0);
   B200_LAUNCH_OK();
+  if (external && side != nullptr && ev_fork != nullptr && ev_join != nullptr) B200_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   return B200_OK;
 }
 

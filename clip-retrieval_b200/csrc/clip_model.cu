@@ -99,6 +99,8 @@ struct b200_clip {
   void* g_out = nullptr;
   bool use_graphs = true;      // B200_GRAPHS=0 disables (A/B, debugging)
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t s_side = nullptr;             // side stream of the attention's leftover-row kernel (fork / join per layer)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fuse_ln = false;        // LayerNorm folded into the qkv / fc GEMMs (B200_FUSE_LN=1): correct, but measured slower than the LN kernel it removes
   int attn_gen = 2;            // 3: attention_tc3.cu (single score pass); 2: attention_tc2.cu (B200_ATTN_GEN; default 2 until verified)
   bool attn_pipelined = true;  // two query tiles in flight (attention_tc2.cu) where the shape allows
@@ -241,7 +243,7 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     B200_TRY(run_linear(m, fused ? t.tm_x : t.tm_h, L.qkv, M, e1, st, CLS_G_QKV, &t.ts_qkv));
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
-        B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st));
+        B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join));
       else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
         B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
@@ -464,6 +466,9 @@ int b200_clip_create(const b200_clip_config* cfg, int device, b200_clip** out) {
     m->allocs.push_back(m->stage_in);
     B200_CUDA(cudaMalloc(&m->stage_out, (size_t)cfg->max_batch * cfg->embed_dim * 4));
     m->allocs.push_back(m->stage_out);
+    B200_CUDA(cudaStreamCreateWithFlags(&m->s_side, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     const int gb = std::min(GRAPH_MAX_B, cfg->max_batch);
     B200_CUDA(cudaMalloc(&m->g_in, std::max((size_t)gb * 3 * cfg->image_size * cfg->image_size * 4, (size_t)gb * cfg->context_length * 8)));
     m->allocs.push_back(m->g_in);
@@ -489,6 +494,9 @@ int b200_clip_destroy(b200_clip* m) {
   if (m->act_ev) cudaEventDestroy(m->act_ev);
   for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->s_side) cudaStreamDestroy(m->s_side);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->s_copy) {
     cudaStreamDestroy(m->s_copy); cudaStreamDestroy(m->s_comp);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_done[i]); }

@@ -33,8 +33,11 @@ int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloa
 // Third generation (attention_tc3.cu): one pass over the scores (Cauchy-Schwarz bound instead of the row maximum),
 // leftover query rows (T mod 128 <= 8) on the FMA pipe, per-sample 3-D tensor map tm3 over qkv [B, T, 3w], box 128x64.
 bool attention_tc3_supported(int T, int heads, int w);
+// side / ev_fork / ev_join (optional): the leftover query rows (T mod 128 <= 4) run as a small kernel on `side`
+// concurrently with the tensor-core kernel; without them they run on `st` before it.
 int attention_tc3(const CUtensorMap& tm3, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* kmax_scratch /*[B*heads]*/,
-                  int B, int T, int heads, int w, int causal, int sms, cudaStream_t st);
+                  int B, int T, int heads, int w, int causal, int sms, cudaStream_t st, cudaStream_t side = nullptr,
+                  cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 // K8/K10/K11: pooled row (x[b*T + pool_index(b)]) -> LN -> @ proj [w, D] -> optional L2 normalise
 // -> fp16 or fp32.  pool_idx == nullptr pools token 0 (vision); else row pool_idx[b] (text EOT).
 int pool_ln_proj_norm(const __nv_bfloat16* x, int T, int w, const int* pool_idx, const float* gamma, const float* beta,
