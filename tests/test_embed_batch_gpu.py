@@ -92,7 +92,7 @@ def test_pair_and_single_cta_gemm_agree_inside_the_model_at_batch_1024():
         assert (1 - clip_ref.cosine(a, b)).max() <= 2e-5
         assert np.abs(a - b).max() <= 4e-3   # a few fp16/bf16 ulps of unit-norm components
     # and the batch-1024 result agrees with the oracle on a handful of samples spread over the batch
-    sel = [0, 1, 255, 256, 511, 1023]
+    sel = [0, 511, 1023]
     sd = {k: v for k, v in m.synthetic_state_dict(arch, seed=0).items()}
     ref_i = clip_ref.mapper_image(sd, cfg, px[sel].cpu())
     ref_t = clip_ref.mapper_text(sd, cfg, tk[sel].cpu())
@@ -101,7 +101,7 @@ def test_pair_and_single_cta_gemm_agree_inside_the_model_at_batch_1024():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("B", [600, 64])
+@pytest.mark.parametrize("B", [600])
 def test_pipelined_host_entry_matches_device_entry(B):
     """encode_host with max_batch >= 256 splits images into four sub-batch slots (H2D on the copy stream
     overlapping compute) and loops over chunks of max_batch; B = 600 = 256 + 256 + 88 leaves a ragged last

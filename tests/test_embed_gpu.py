@@ -110,9 +110,9 @@ def test_vit_l14_matches_oracle():
     import torch
 
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    model, cfg, sd = _model("ViT-L/14", 3)
-    px = clip_ref.synth_images(3, cfg, seed=1)
-    tk = clip_ref.synth_tokens(3, cfg, seed=1)
+    model, cfg, sd = _model("ViT-L/14", 2)
+    px = clip_ref.synth_images(2, cfg, seed=1)
+    tk = clip_ref.synth_tokens(2, cfg, seed=1)
     ei, et = model.embed_image(px), model.embed_text(tk)
     ci = 1 - clip_ref.cosine(ei, clip_ref.mapper_image(sd, cfg, px))
     ct = 1 - clip_ref.cosine(et, clip_ref.mapper_text(sd, cfg, tk))
