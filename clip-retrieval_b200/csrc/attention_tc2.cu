@@ -8,7 +8,10 @@
 // has consumed them, for its output O (columns 0..63 of the same buffer).  Two softmax groups of 4
 // warps alternate tiles, so S(t+1) and P.V(t-1) run on the tensor pipe while group (t & 1) is in its
 // exp pass.  Keys past 256 (the cls token makes T = 257) never touch the tensor core: their scores
-// q.k_e and their p_e*v_e contributions are a 64-term dot product per row on the FMA pipe.
+// q.k_e and their p_e*v_e contributions are a 64-term dot product per row on the FMA pipe; the q rows
+// come out of the (double-buffered) Q tile in shared memory — read from global memory they put ~1 us
+// of uncoalesced-load latency in front of every tile's softmax (profiles/r02h: the 257th KEY cost as
+// much as the padded third query tile).
 //
 //   warp 8      TMA: K, V rows of the head (128-row boxes) once per (sample, head),
 //               Q tile per 128 query rows; all straight out of the fused qkv buffer, 128B swizzle.
@@ -28,7 +31,7 @@ constexpr int A2_MAXT = 264;                      // 256 keys on the tensor core
 constexpr int A2_Q_BYTES = 128 * 128;             // 16 KB
 constexpr int A2_KV_MAIN = 2 * 128 * 128;         // 256 rows x 128 B
 constexpr int A2_P_BYTES = 4 * 128 * 128;         // 4 key blocks of [128 rows x 64 keys] per group
-constexpr int A2_SMEM = A2_Q_BYTES + 2 * A2_KV_MAIN + 2 * A2_P_BYTES + 256 + 1024;
+constexpr int A2_SMEM = 2 * A2_Q_BYTES + 2 * A2_KV_MAIN + 2 * A2_P_BYTES + 256 + 1024;   // Q tile double-buffered
 constexpr int A2_THREADS = 320;
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
@@ -38,22 +41,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = base;
-  uint8_t* sK = sQ + A2_Q_BYTES;               // rows 0..255
+  uint8_t* sQ = base;                          // [2] query tiles: tile tc lives in buffer tc & 1 (= its softmax group)
+  uint8_t* sK = sQ + 2 * A2_Q_BYTES;           // rows 0..255
   uint8_t* sV = sK + A2_KV_MAIN;               // rows 0..255
   uint8_t* sP = sV + A2_KV_MAIN;               // [2 groups][4 key blocks][128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A2_P_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;
-  uint64_t* k_free = bars + 3;
-  uint64_t* v_full = bars + 4;
-  uint64_t* v_free = bars + 5;
-  uint64_t* s_full = bars + 6;    // [2]
-  uint64_t* p_full = bars + 8;    // [2]
-  uint64_t* o_full = bars + 10;   // [2]
-  uint64_t* buf_free = bars + 12; // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 2;   // [2]  MMA commit (S of the tile done) [+ the 4 softmax warps that read their q rows]
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_free = bars + 5;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_free = bars + 7;
+  uint64_t* s_full = bars + 8;    // [2]
+  uint64_t* p_full = bars + 10;   // [2]
+  uint64_t* o_full = bars + 12;   // [2]
+  uint64_t* buf_free = bars + 14; // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int keys_main = T < 256 ? (T + 15) / 16 * 16 : 256;  // keys on the tensor core (multiple of 16)
@@ -67,8 +70,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   }
   if (warp == 9) {
     if (lane == 0) {
-      for (int i = 0; i < 6; i++) ptx::mbar_init(&bars[i], 1);
+      for (int i = 4; i < 8; i++) ptx::mbar_init(&bars[i], 1);
       for (int i = 0; i < 2; i++) {
+        ptx::mbar_init(&q_full[i], 1);
+        // keys past 256 are scored on the FMA pipe from the q rows in shared memory: the tile's softmax warps hold it too
+        ptx::mbar_init(&q_empty[i], extra > 0 ? 5 : 1);
         ptx::mbar_init(&s_full[i], 1);
         ptx::mbar_init(&p_full[i], 4);
         ptx::mbar_init(&o_full[i], 1);
@@ -98,9 +104,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         for (int i = 0; i < kv_boxes; i++)
           ptx::tma_load_2d(sK + i * 128 * 128, &tmBig, k_full, w + h * A2_HD, b * T + i * 128);
         for (int mt = 0; mt < q_tiles; mt++, tc++) {
-          ptx::mbar_wait(q_empty, (tc & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(q_full, A2_Q_BYTES);
-          ptx::tma_load_2d(sQ, &tmBig, q_full, h * A2_HD, b * T + mt * 128);
+          ptx::mbar_wait(&q_empty[tc & 1], ((tc >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&q_full[tc & 1], A2_Q_BYTES);
+          ptx::tma_load_2d(sQ + (tc & 1) * A2_Q_BYTES, &tmBig, &q_full[tc & 1], h * A2_HD, b * T + mt * 128);
           if (mt == 0) {
             // V of this head (free once the previous head's last P.V has completed)
             ptx::mbar_wait(v_free, (it & 1) ^ 1);
@@ -141,15 +147,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         for (int mt = 0; mt < q_tiles; mt++, tc++) {
           const int bsel = tc & 1;
           if (mt == 0) ptx::mbar_wait(k_full, it & 1);
-          ptx::mbar_wait(q_full, tc & 1);
+          ptx::mbar_wait(&q_full[bsel], (tc >> 1) & 1);
           ptx::mbar_wait(&buf_free[bsel], ((tc >> 1) & 1) ^ 1);   // O(tc-2) has been read out of this buffer
           ptx::tc_fence_after();
-          const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
+          const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ + bsel * A2_Q_BYTES));
           const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
 #pragma unroll
           for (int k = 0; k < A2_HD / 16; k++)
             ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
-          ptx::umma_commit(q_empty);
+          ptx::umma_commit(&q_empty[bsel]);
           ptx::umma_commit(&s_full[bsel]);
           if (mt == q_tiles - 1) ptx::umma_commit(k_free);
           if (have_prev) issue_pv(prev_tc, prev_first, prev_last, prev_it);
@@ -182,6 +188,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
           // every row of this warp lies past the sequence (T = 257: three of the four warps of the third tile):
           // no scores to read, no exponentials, nothing to store — the P rows it would have written only feed
           // output rows nobody keeps.  It still takes part in the hand-shakes of the tile.
+          if (extra > 0 && lane == 0) ptx::mbar_arrive(&q_empty[grp]);   // never reads the q rows: its share is free
           ptx::mbar_wait(&s_full[grp], n & 1);
           ptx::tc_fence_after();
           ptx::fence_proxy_async();
@@ -201,12 +208,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
 #pragma unroll
         for (int e = 0; e < 8; e++) se[e] = -INFINITY;
         if (extra > 0) {
+          // this thread's query row out of the Q tile the TMA staged for the MMA (buffer = group): ~30 cycles of
+          // shared-memory latency instead of a ~1 us uncoalesced global read in front of every tile's softmax
           float qf[A2_HD];
-          const int qr = qrow < T ? qrow : T - 1;
-          const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + qr) * 3 * w + (size_t)h * A2_HD);
+          ptx::mbar_wait(&q_full[grp], n & 1);
+          const uint8_t* qrow_s = sQ + grp * A2_Q_BYTES + r * 128;
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            const uint4 u = qp[c];
+            const uint4 u = *reinterpret_cast<const uint4*>(qrow_s + ((c ^ (r & 7)) * 16));
             const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
             qf[c * 8 + 0] = a0.x; qf[c * 8 + 1] = a0.y; qf[c * 8 + 2] = a1.x; qf[c * 8 + 3] = a1.y;
             qf[c * 8 + 4] = a2.x; qf[c * 8 + 5] = a2.y; qf[c * 8 + 6] = a3.x; qf[c * 8 + 7] = a3.y;
@@ -228,6 +237,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
             for (int ee = 0; ee < 8; ee++)
               if (ee == e) se[ee] = (256 + e <= kmax) ? acc : -INFINITY;
           }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&q_empty[grp]);   // this warp's q rows are in registers
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
