@@ -1,15 +1,17 @@
 #!/usr/bin/env python
 """bench.py — the BASELINE.json configs on B200, one JSON line (contract: DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload all|vitl14|knn|ivf|e2e]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload all|vitl14|knn|ivf|e2e|plumbing]
 
-Workloads (BASELINE.json `configs`; configs[0] is the CPU plumbing case covered by tests/):
+Workloads (BASELINE.json `configs`):
+  plumbing configs[0] ViT-B/32 clip_inference on 100 synthetic images + captions through the reference's own reader /
+                      runner / writer (baseline/_ref, unmodified) around the CUDA ClipMapper     -> samples/s
   vitl14  configs[1]  ViT-L/14 image+text inference, synthetic 224^2, batch 1024 per GPU   -> pairs/s
   knn     configs[2]  brute-force cosine kNN, 100M x 768 fp16 rows per GPU, 1000 queries, top-40 -> queries/s
   ivf     configs[3]  IVF-Flat (nlist 65536, nprobe 16/64), rows range-sharded over the ranks, one all-gather -> queries/s
   e2e     configs[4]  clip_back query path: ViT-H/14 text -> embed -> sharded IVF kNN -> ids on the host, p50/p99 + QPS
-`--workload all` (the default) prints the vitl14 line (the headline metric's first half) with the other three
-nested under "knn", "ivf", "e2e_query" — each a complete sub-line with its own `roofline`, `cpu_baseline`,
+`--workload all` (the default) prints the vitl14 line (the headline metric's first half) with the other four
+nested under "knn", "ivf", "e2e_query", "plumbing" — each a complete sub-line with its own `roofline`, `cpu_baseline`,
 `e2e` and `parity_checked`.  `--workload X` prints X's line alone.
 
 Per line: `value` = whole-job throughput with inputs resident in HBM (CUDA events, barrier + sync both sides,
@@ -931,14 +933,210 @@ def cpu_baseline_e2e(ctx, arch, d, k, nprobe, rows_gpu, nlist_gpu, nquery=8):
 
 
 # ---- the B200 arm ---------------------------------------------------------------------------------------------
-WORKLOADS = {"vitl14": wl_vitl14, "knn": wl_knn, "ivf": wl_ivf, "e2e": wl_e2e}
-NEST_KEY = {"knn": "knn", "ivf": "ivf", "e2e": "e2e_query"}
+# ---- configs[0]: the clip_inference plumbing (reference reader -> runner -> mapper -> writer) -------------------
+REF_INFERENCE = os.path.join(ROOT, "baseline", "_ref", "clip_retrieval", "clip_inference")
+
+
+def ref_inference_module(name):
+    """reader.py / runner.py / writer.py of the UNMODIFIED reference install under baseline/_ref, loaded by file path
+    (the package's __init__ imports flask/faiss/all_clip, which are not installable offline; these three files only
+    need torch, PIL, fsspec and pyarrow)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF_INFERENCE, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def hashed_tokenizer(texts, context_length=77, vocab=49408):
+    """Stands in for the CLIP BPE tokenizer (its vocabulary file cannot be downloaded here): SOT, one hashed id per
+    word, EOT (the largest id, which is what the text tower's argmax pooling looks for)."""
+    import torch
+
+    out = torch.zeros(len(texts), context_length, dtype=torch.int64)
+    for i, t in enumerate(texts):
+        ids = [1 + ((sum(w.encode()) * 31 + j) % (vocab - 408)) for j, w in enumerate(t.split())][:context_length - 2]
+        out[i, 0] = vocab - 2
+        if ids:
+            out[i, 1:1 + len(ids)] = torch.tensor(ids, dtype=torch.int64)
+        out[i, 1 + len(ids)] = vocab - 1
+    return out
+
+
+def make_plumbing_dataset(folder, n, seed=0):
+    """`n` synthetic images (every third exactly 224x224, the rest ragged so Resize/CenterCrop do work) + captions."""
+    import numpy as np
+    from PIL import Image
+
+    os.makedirs(folder, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        h, w = (224, 224) if i % 3 == 0 else (200 + i % 150, 260 + (i * 7) % 90)
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(os.path.join(folder, "%04d.png" % i))
+        with open(os.path.join(folder, "%04d.txt" % i), "w") as f:
+            f.write("a photo of object %d" % i)
+
+
+def run_reference_runner(src, out_root, mapper, preprocess, tokenizer, parts=2, batch_size=32):
+    """One clip_inference job through the reference's own FilesReader, Runner and NumpyWriter (runner.py:17-62):
+    the reference keys files by path INCLUDING the extension (reader.py:17-32), so image and caption keys never
+    intersect and a folder job is one pass over the images and one over the captions (as its own tests do,
+    test_reader.py:39).  `mapper` is the ClipMapper-contract callable under test.  Returns seconds inside mapper()."""
+    reader, runner, writer = ref_inference_module("reader"), ref_inference_module("runner"), ref_inference_module("writer")
+    spent = [0.0]
+
+    class Logger:
+        def start(self): pass
+        def end(self): pass
+        def __call__(self, stats): pass
+
+    for modality in ("image", "text"):
+        img, txt = modality == "image", modality == "text"
+
+        def call(batch, img=img, txt=txt):
+            t0 = time.perf_counter()
+            r = mapper(batch, img, txt)
+            spent[0] += time.perf_counter() - t0
+            return r
+
+        out = os.path.join(out_root, "out_" + modality)
+        run = runner.Runner(
+            reader_builder=lambda sampler, img=img, txt=txt: reader.FilesReader(
+                sampler, preprocess, tokenizer, src, batch_size, 0, enable_text=txt, enable_image=img, enable_metadata=False),
+            mapper_builder=lambda call=call: call,
+            writer_builder=lambda i, out=out, img=img, txt=txt: writer.NumpyWriter(
+                partition_id=i, output_folder=out, enable_text=txt, enable_image=img, enable_metadata=False,
+                output_partition_count=parts),
+            logger_builder=lambda i: Logger(),
+            output_partition_count=parts,
+        )
+        for i in range(parts):
+            run(i)
+    return spent[0]
+
+
+def read_plumbing_output(out_root):
+    import numpy as np
+    from clip_retrieval_b200.index import list_embedding_shards
+
+    img = [np.load(f) for f in list_embedding_shards(os.path.join(out_root, "out_image", "img_emb"))]
+    txt = [np.load(f) for f in list_embedding_shards(os.path.join(out_root, "out_text", "text_emb"))]
+    return img, txt
+
+
+def wl_plumbing(ctx):
+    """BASELINE configs[0]: ViT-B/32 clip_inference on 100 synthetic images + captions — the reference's reader,
+    runner and writer, unmodified, around the CUDA `ClipMapper`; the CPU arm is the same job around the fp32 oracle."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    m = ctx.m
+    n, parts, bs = 100, 2, 32
+    base = {"metric": "ViT-B/32 clip_inference samples/s (image + caption files -> fp16 .npy shards)", "unit": "samples/s",
+            "n_gpus": ctx.world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ViT-B/32 clip_inference on %d synthetic images + captions per GPU through the reference's own FilesReader / "
+                                   "Runner / NumpyWriter (baseline/_ref, unmodified), batch %d, %d output partitions (BASELINE configs[0])"
+                                   % (n, bs, parts)}}
+    if not os.path.isdir(REF_INFERENCE):
+        base.update({"unavailable": "baseline/_ref (the reference install, made by __graft_entry__.build() where /root/reference exists) "
+                                    "is not in this tree", "parity_checked": None})
+        return base
+    tmp = tempfile.mkdtemp(prefix="b200clip_plumbing_%d_" % ctx.rank)
+    try:
+        src = os.path.join(tmp, "images")
+        make_plumbing_dataset(src, n)
+        mapper = m.ClipMapper(enable_image=True, enable_text=True, enable_metadata=False, use_mclip=False,
+                              clip_model="synthetic:ViT-B/32", use_jit=True, mclip_model="", warmup_batch_size=bs)
+        arch = mapper.model.arch
+        from clip_retrieval_b200.model import make_preprocess
+
+        preprocess = make_preprocess(arch.image_size)
+
+        def cuda_mapper(batch, img, txt):
+            mapper.enable_image, mapper.enable_text = img, txt
+            return mapper(batch)
+
+        steps, times, inside = max(1, min(ctx.args.steps, 3)), [], []
+        launches0 = None
+        for it in range(1 + steps):                                      # one warm-up job, then `steps` timed jobs
+            out = os.path.join(tmp, "gpu_%d" % it)
+            ctx.barrier()
+            if it == 1:
+                launches0 = m.launch_count()
+            t0 = time.perf_counter()
+            sec = run_reference_runner(src, out, cuda_mapper, preprocess, hashed_tokenizer, parts, bs)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it:
+                times.append(ctx.max_over_ranks(dt))
+                inside.append(sec)
+        launches = (m.launch_count() - launches0) // steps
+        t_job = statistics.median(times)
+        img_g, txt_g = read_plumbing_output(os.path.join(tmp, "gpu_1"))
+        ok_layout = (len(img_g) == parts and len(txt_g) == parts
+                     and all(a.dtype == np.float16 and a.shape == (n // parts, arch.embed_dim) for a in img_g + txt_g))
+        res = dict(base)
+        res.update({"value": ctx.world * n / t_job, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * t_job,
+                    "gpu_launches": int(launches),
+                    "e2e": {"value": ctx.world * n / t_job, "unit": "samples/s",
+                            "h2d_bytes_per_step": n * (3 * arch.image_size ** 2 * 4 + arch.context_length * 8),
+                            "d2h_bytes_per_step": 2 * n * arch.embed_dim * 2},
+                    "mapper_ms_per_step": 1e3 * statistics.median(inside),
+                    "note": "host-bound by design: PNG decode + torchvision Resize/CenterCrop run in the reference's DataLoader "
+                            "(num_workers 0) on one host thread; `mapper_ms_per_step` is the part this engine replaces "
+                            "(H2D, both towers, normalise, fp16, D2H for %d images and %d captions)" % (n, n)})
+        res["roofline"] = None
+        if ctx.rank == 0 and not ctx.args.no_cpu:
+            from oracle import clip_ref
+
+            cfg = clip_ref.CONFIGS["ViT-B/32"]
+            sd = m.synthetic_state_dict(arch, seed=0)
+            cores = physical_cores()
+            torch.set_num_threads(cores)
+
+            def cpu_mapper(batch, img, txt):
+                return {"image_embs": clip_ref.mapper_image(sd, cfg, batch["image_tensor"]) if img else None,
+                        "text_embs": clip_ref.mapper_text(sd, cfg, batch["text_tokens"]) if txt else None,
+                        "image_filename": batch["image_filename"] if img else None, "text": batch["text"] if txt else None,
+                        "metadata": None}
+
+            clip_ref.mapper_image(sd, cfg, clip_ref.synth_images(2, cfg)); clip_ref.mapper_text(sd, cfg, clip_ref.synth_tokens(2, cfg))  # warm-up
+            t0 = time.perf_counter()
+            sec_cpu = run_reference_runner(src, os.path.join(tmp, "cpu"), cpu_mapper, preprocess, hashed_tokenizer, parts, bs)
+            dt_cpu = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": n / dt_cpu, "unit": "samples/s", "cores": cores, "kind": "port",
+                                   "mapper_ms_per_step": 1e3 * sec_cpu,
+                                   "sample": "the same %d-sample job once, same reference reader/runner/writer, mapper = fp32 oracle/clip_ref.py "
+                                             "with %d torch threads (the reference's own mapper needs all_clip/open_clip, not installable)"
+                                             % (n, cores)}
+            img_c, txt_c = read_plumbing_output(os.path.join(tmp, "cpu"))
+            worst = 0.0
+            for a, b in zip(img_g + txt_g, img_c + txt_c):
+                worst = max(worst, float((1 - clip_ref.cosine(a, b)).max()))
+            res["parity"] = {"shard_layout_as_reference_writer": bool(ok_layout), "max_1_minus_cos_vs_oracle_job": worst,
+                             "embeddings_within_1e-3_cosine": bool(worst <= 1e-3)}
+            ok = ok_layout and worst <= 1e-3
+        else:
+            res["parity"] = {"shard_layout_as_reference_writer": bool(ok_layout)}
+            ok = ok_layout
+        res["parity_checked"] = ctx.all_true(ok)
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+WORKLOADS = {"vitl14": wl_vitl14, "knn": wl_knn, "ivf": wl_ivf, "e2e": wl_e2e, "plumbing": wl_plumbing}
+NEST_KEY = {"knn": "knn", "ivf": "ivf", "e2e": "e2e_query", "plumbing": "plumbing"}
 
 
 def run_b200(args):
     ctx = Ctx(args)
-    names = ["vitl14", "knn", "ivf", "e2e"] if args.workload == "all" else [args.workload]
-    for skip, flag in (("knn", args.no_knn), ("ivf", args.no_ivf), ("e2e", args.no_e2e)):
+    names = ["vitl14", "knn", "ivf", "e2e", "plumbing"] if args.workload == "all" else [args.workload]
+    for skip, flag in (("knn", args.no_knn), ("ivf", args.no_ivf), ("e2e", args.no_e2e), ("plumbing", args.no_plumbing)):
         if flag and skip in names and len(names) > 1:
             names.remove(skip)
     results = {}
@@ -950,7 +1148,7 @@ def run_b200(args):
     for n in names[1:]:
         top[NEST_KEY[n]] = results[n]
     if len(names) > 1:
-        top["parity_checked_all"] = all(bool(results[n].get("parity_checked")) for n in names)
+        top["parity_checked_all"] = all(bool(results[n].get("parity_checked")) for n in names if results[n].get("parity_checked") is not None)
     if ctx.rank == 0:
         emit(top)
     if ctx.world > 1:
@@ -1021,7 +1219,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "vitl14", "knn", "ivf", "e2e"])
+    ap.add_argument("--workload", default="all", choices=["all", "vitl14", "knn", "ivf", "e2e", "plumbing"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
@@ -1029,6 +1227,7 @@ def main():
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-ivf", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-plumbing", action="store_true")
     ap.add_argument("--knn-rows", type=int, default=100_000_000)
     ap.add_argument("--knn-nq", type=int, default=1000)
     ap.add_argument("--knn-steps", type=int, default=2)

@@ -23,6 +23,7 @@
 #include "embed_kernels.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -37,7 +38,7 @@ constexpr int A2_THREADS = 320;
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
                      const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int T, int heads,
-                     int w, float scale_log2e, int causal) {
+                     int w, float scale_log2e, int causal, int tail_external) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -62,7 +63,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   const int keys_main = T < 256 ? (T + 15) / 16 * 16 : 256;  // keys on the tensor core (multiple of 16)
   const int extra = T > 256 ? T - 256 : 0;                    // keys handled on the FMA pipe
   const int kv_boxes = (keys_main + 127) / 128;
-  const int q_tiles = (T + 127) / 128;
+  // tail_external: the last T mod 128 query rows (1..4 of them, after at least one full tile) are computed by
+  // attention_tail_kernel next to this kernel instead of a padded 128-row tile of their own
+  const int q_tiles = tail_external ? T / 128 : (T + 127) / 128;
   const int items = B * heads;
 
   if (warp == 8 && lane == 0) {
@@ -358,7 +361,7 @@ bool attention_tc2_supported(int T, int heads, int w) {
 }
 
 int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
-                  int causal, int sms, cudaStream_t st) {
+                  int causal, int sms, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join, int tail_mode) {
   B200_CHECK(attention_tc2_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc2: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
   if (B == 0) return B200_OK;
@@ -372,8 +375,24 @@ int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloa
   const float scale_log2e = (1.0f / sqrtf((float)A2_HD)) * 1.4426950408889634f;
   const int items = B * heads;
   const int grid = items < sms ? items : sms;
-  attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM, st>>>(tmBig, qkv, out, B, T, heads, w, scale_log2e, causal);
+  // T = 257: two full tiles on the tensor cores and ONE leftover row.  As a third 128-row tile that row costs
+  // 0.36 ms per ViT-L/14 layer at batch 1024 (T = 256: 0.769 ms, T = 257: 1.131 ms).  Moving it to a small kernel on a
+  // second stream was measured and LOSES (1.391 ms stand-alone, attention 38.1 -> 43.1 ms per step in the model,
+  // profiles/r02j_attention_tail_ab.txt): the warp-per-row kernel re-reads K and V of its head from L2 for one row
+  // (0.45 ms on its own) and competes with the tensor-core kernel for the same SMs.  Kept behind
+  // B200_ATTN_TAIL_KERNEL=1 for the record; the default computes every row on the tensor cores.
+  static const bool tail_on = getenv("B200_ATTN_TAIL_KERNEL") != nullptr && atoi(getenv("B200_ATTN_TAIL_KERNEL")) != 0;
+  const int n_full = T / 128, rem = T - n_full * 128;
+  const bool external = (tail_mode < 0 ? tail_on : tail_mode != 0) && side != nullptr && ev_fork != nullptr && ev_join != nullptr && rem > 0 && rem <= 4 && n_full >= 1;
+  if (external) {
+    B200_CUDA(cudaEventRecord(ev_fork, st));
+    B200_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    B200_TRY(attention_tail_rows(qkv, out, B, T, heads, w, causal, n_full * 128, rem, side));
+    B200_CUDA(cudaEventRecord(ev_join, side));
+  }
+  attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM, st>>>(tmBig, qkv, out, B, T, heads, w, scale_log2e, causal, external ? 1 : 0);
   B200_LAUNCH_OK();
+  if (external) B200_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   return B200_OK;
 }
 

@@ -601,6 +601,18 @@ attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + trow) * w + (size_t)h * A3_HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
+int attention_tail_rows(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w, int causal, int row0,
+                        int nrows, cudaStream_t st) {
+  B200_CHECK(heads > 0 && w / heads == A3_HD && T <= A3_MAXT && nrows >= 1 && row0 + nrows <= T, B200_ERR_UNSUPPORTED,
+             "attention_tail_rows: unsupported shape T=%d hd=%d rows %d..%d", T, heads ? w / heads : 0, row0, row0 + nrows);
+  if (B == 0) return B200_OK;
+  const float scale_log2e = (1.0f / sqrtf((float)A3_HD)) * 1.4426950408889634f;
+  const unsigned nw = (unsigned)((size_t)B * heads * nrows);
+  attention_tail_kernel<<<(nw + 3) / 4, 128, 0, st>>>(qkv, out, B, T, heads, w, scale_log2e, causal, row0, nrows);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
 bool attention_tc3_supported(int T, int heads, int w) {
   return heads > 0 && w % heads == 0 && w / heads == A3_HD && T >= 1 && T <= A3_MAXT;
 }

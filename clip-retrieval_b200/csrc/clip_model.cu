@@ -245,7 +245,7 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
         B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join));
       else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
-        B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st));
+        B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join));
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
@@ -737,7 +737,22 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
     return attention_tc3(t3, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, scratch[device & 63], B, T, heads, w, causal,
                          sm_count(device), (cudaStream_t)stream);
   }
-  // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu)
+  // Tp == -3: attention_tc2 with the leftover rows (T mod 128 in 1..4) on a second stream, as the model runs it
+  if (Tp == -3) {
+    static std::mutex smu;
+    static cudaStream_t side[64] = {};
+    static cudaEvent_t ev[64][2] = {};
+    std::lock_guard<std::mutex> lock(smu);
+    const int d = device & 63;
+    if (!side[d]) {
+      B200_CUDA(cudaStreamCreateWithFlags(&side[d], cudaStreamNonBlocking));
+      B200_CUDA(cudaEventCreateWithFlags(&ev[d][0], cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&ev[d][1], cudaEventDisableTiming));
+    }
+    return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
+                         (cudaStream_t)stream, side[d], ev[d][0], ev[d][1], 1);
+  }
+  // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu), every row on the tensor cores
   if (Tp < 0)
     return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
                          (cudaStream_t)stream);

@@ -28,8 +28,16 @@ int attention_tc(const CUtensorMap& tmQK, const CUtensorMap& tmVt, __nv_bfloat16
                  int causal, int v_direct, int sms, cudaStream_t st);
 // Two-tiles-in-flight variant (attention_tc2.cu): head dim 64, T <= 264; V read from the qkv buffer.
 bool attention_tc2_supported(int T, int heads, int w);
+// side / ev_fork / ev_join + tail_mode 1 (or -1 and B200_ATTN_TAIL_KERNEL=1): when T leaves 1..4 query rows after the last
+// full 128-row tile (T = 257), those rows run as attention_tail_rows on `side`, concurrently with the tensor-core kernel,
+// instead of a padded tile.  Measured slower (profiles/r02j_attention_tail_ab.txt): off by default.
 int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
-                  int causal, int sms, cudaStream_t st);
+                  int causal, int sms, cudaStream_t st, cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr,
+                  cudaEvent_t ev_join = nullptr, int tail_mode = -1);
+// Query rows row0 .. row0 + nrows - 1 of every (sample, head) on the FMA pipe: one warp per row, exact two-pass softmax,
+// K and V from the qkv buffer (attention_tc3.cu).
+int attention_tail_rows(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w, int causal, int row0,
+                        int nrows, cudaStream_t st);
 // Third generation (attention_tc3.cu): one pass over the scores (Cauchy-Schwarz bound instead of the row maximum),
 // leftover query rows (T mod 128 <= 8) on the FMA pipe, per-sample 3-D tensor map tm3 over qkv [B, T, 3w], box 128x64.
 bool attention_tc3_supported(int T, int heads, int w);

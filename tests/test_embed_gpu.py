@@ -166,7 +166,7 @@ def test_zero_feature_row_is_nan_like_reference():
 
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("B,T,heads,causal", [(2, 257, 16, 0), (3, 77, 8, 1), (2, 50, 12, 0), (1, 1, 2, 0), (5, 128, 4, 1),
-                                              (1, 320, 2, 0), (40, 257, 16, 0), (3, 260, 2, 0), (2, 256, 2, 1), (7, 129, 3, 0)])
+                                              (1, 320, 2, 0), (40, 257, 16, 0), (3, 260, 2, 0), (2, 256, 2, 1), (7, 129, 3, 0), (2, 258, 3, 1)])
 def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
     """tcgen05 attention (TMA K / V^T tiles, scores and output in TMEM, P through swizzled shared
     memory) against a plain fp32 PyTorch softmax(QK^T)V of the same bf16 inputs."""
@@ -205,6 +205,14 @@ def test_tcgen05_attention_matches_fp32_reference(B, T, heads, causal):
         err3 = (out3.float() - ref).abs()
         assert not torch.isnan(out3.float()).any()
         assert bool((err3 <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc2 max err %g" % err3.max().item()
+        # the same kernel with the leftover rows (T mod 128 in 1..4) in attention_tail_rows on a second stream
+        out3b = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+        check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -3, out3b.data_ptr(), B, T, heads, w, causal, 0,
+                                                torch.cuda.current_stream().cuda_stream), "attention_tc2+tail")
+        torch.cuda.synchronize()
+        err3b = (out3b.float() - ref).abs()
+        assert not torch.isnan(out3b.float()).any()
+        assert bool((err3b <= ref.abs() * 2 ** -7 + 2e-2).all()), "tc2+tail max err %g" % err3b.max().item()
         # fourth variant (production): one score pass against a Cauchy-Schwarz bound, leftover rows on the FMA pipe
         out4 = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
         check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -2, out4.data_ptr(), B, T, heads, w, causal, 0,
@@ -232,7 +240,7 @@ def test_tcgen05_attention_second_key_block_dominates():
     out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
     q, k, vv = qkv.float().view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, -1) @ vv).transpose(1, 2).reshape(B * T, w)
-    for gen in (-1, -2):
+    for gen in (-1, -3, -2):
         out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
         check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, gen, out.data_ptr(), B, T, heads, w, 0, 0,
                                                 torch.cuda.current_stream().cuda_stream), "attention_tc%d" % (1 - gen))

@@ -17,7 +17,7 @@ for name, T, heads, causal in shapes:
     qkv = torch.randn(B * T, 3 * w, device="cuda").bfloat16()
     out = torch.empty(B * T, w, device="cuda", dtype=torch.bfloat16)
     res = {}
-    for gen in (-1, -2):
+    for gen in (-1, -3, -2):
         for _ in range(3):
             check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, gen, out.data_ptr(), B, T, heads, w, causal, 0, st), "attn")
         torch.cuda.synchronize()
