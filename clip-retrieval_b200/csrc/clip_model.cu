@@ -761,6 +761,8 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
                       (cudaStream_t)stream);
 }
 
+int b200_attention_set_variant(int variant) { return attention_tc2_set_variant(variant); }
+
 int b200_clip_set_profiling(b200_clip* m, int on) {
   B200_CHECK(m, B200_ERR_INVALID, "set_profiling: null handle");
   m->profiling = on != 0;

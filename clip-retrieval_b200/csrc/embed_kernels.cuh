@@ -34,6 +34,7 @@ bool attention_tc2_supported(int T, int heads, int w);
 int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
                   int causal, int sms, cudaStream_t st, cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr,
                   cudaEvent_t ev_join = nullptr, int tail_mode = -1);
+int attention_tc2_set_variant(int v);   // returns the previous variant; v < 0 only reads it
 // Query rows row0 .. row0 + nrows - 1 of every (sample, head) on the FMA pipe: one warp per row, exact two-pass softmax,
 // K and V from the qkv buffer (attention_tc3.cu).
 int attention_tail_rows(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w, int causal, int row0,

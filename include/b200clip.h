@@ -236,6 +236,11 @@ int b200_gemm_set_pair_mode(int on);
 /* CTA-pair kernel only: 1 = results (and the residual operand) travel through shared memory and TMA tensor
  * stores / loads instead of per-thread 16-byte global stores / loads; 0 = the register path (A/B, parity tests). */
 int b200_gemm_set_tma_store(int on);
+/* attention_tc2 (head dim 64, T <= 264) softmax-loop variant, for A/B measurements and parity between the variants:
+ * bit 0 = tcgen05.ld of the next 32-column chunk in flight while the current one is processed, bit 1 = unmasked loop
+ * copies for chunks no lane masks, bit 2 / bit 3 = P.V issued per 64 / 128 keys as the softmax writes them (else once per
+ * tile).  Returns the previous variant; a negative argument only reads it. */
+int b200_attention_set_variant(int variant);
 
 /* Stand-alone entries of the two other embed kernels, for their parity tests:
  * LayerNorm (eps 1e-5) over rows of `w` bf16 values; multi-head attention over a fused qkv buffer

@@ -119,6 +119,35 @@ def test_vit_l14_matches_oracle():
     assert ci.max() <= COS_TOL and ct.max() <= COS_TOL, (ci, ct)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,T,heads,causal", [(3, 257, 4, 0), (2, 77, 3, 1), (2, 200, 2, 1), (1, 264, 2, 0), (2, 16, 2, 0)])
+def test_tcgen05_attention_variants_are_bit_identical(B, T, heads, causal):
+    """The softmax-loop variants of attention_tc2 (pipelined tcgen05.ld, unmasked loop copies, block-wise P.V issue)
+    reorder loads and hand-shakes, not arithmetic: every variant must reproduce variant 0 bit for bit."""
+    import torch
+    from clip_retrieval_b200._lib import lib, check
+
+    w = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + heads)
+    qkv = torch.randn(B * T, 3 * w, device="cuda", generator=g).bfloat16()
+    old = lib.b200_attention_set_variant(-1)
+    try:
+        outs = []
+        for v in range(16):
+            lib.b200_attention_set_variant(v)
+            out = torch.full((B * T, w), float("nan"), device="cuda", dtype=torch.bfloat16)
+            for _ in range(2):   # twice: the second launch starts from the barrier phases the first one left
+                check(lib.b200_attention_tc_bf16_device(qkv.data_ptr(), None, -1, out.data_ptr(), B, T, heads, w, causal, 0,
+                                                        torch.cuda.current_stream().cuda_stream), "attention_tc2")
+            torch.cuda.synchronize()
+            assert not torch.isnan(out.float()).any(), "variant %d" % v
+            outs.append(out)
+        for v in range(1, 16):
+            assert torch.equal(outs[0], outs[v]), "variant %d differs from variant 0" % v
+    finally:
+        lib.b200_attention_set_variant(old)
+
+
 @pytest.mark.timeout(300)
 def test_mapper_drop_in_contract():
     """The reference's own mapper test pins shape[0] and dtype float16 (tests/test_clip_inference/

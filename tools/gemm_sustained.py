@@ -40,6 +40,28 @@ def run(name, N, K, bias, res, act, secs=0.6):
           flush=True)
 
 
+def run_cublas(name, N, K, secs=0.6):
+    """The vendor library on the same shape (torch.nn.functional.linear -> cuBLASLt, bias epilogue), same sustained protocol:
+    a per-shape reference point for the hand-written kernel — MEASURED_PEAKS' sustained figure is cuBLAS at a large square shape."""
+    A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda").bfloat16()
+    t0 = time.time()
+    while time.time() - t0 < 0.6:
+        for _ in range(20):
+            torch.nn.functional.linear(A, W, b)
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(20, int(secs / 0.0015))
+    e0.record()
+    for _ in range(reps):
+        torch.nn.functional.linear(A, W, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print("%-7s N=%d K=%d cuBLASLt linear+bias:      %.3f ms  %.0f TFLOP/s" % (name, N, K, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
+
+
 # the four per-layer GEMMs with the epilogue features the model uses: (bias, residual, activation)
 for name, N, K, feats in (("qkv", 3072, 1024, [(1, 0, 0)]),
                           ("out", 1024, 1024, [(1, 0, 0), (1, 1, 0)]),
@@ -47,3 +69,5 @@ for name, N, K, feats in (("qkv", 3072, 1024, [(1, 0, 0)]),
                           ("c_proj", 1024, 4096, [(1, 1, 0)])):
     for bias, res, act in feats:
         run(name, N, K, bias, res, act)
+    if "--cublas" in sys.argv:
+        run_cublas(name, N, K)
