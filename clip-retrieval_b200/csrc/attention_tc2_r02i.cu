@@ -23,7 +23,6 @@
 #include "embed_kernels.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
-#include <cstdlib>
 
 namespace b200 {
 
@@ -34,77 +33,11 @@ constexpr int A2_KV_MAIN = 2 * 128 * 128;         // 256 rows x 128 B
 constexpr int A2_P_BYTES = 4 * 128 * 128;         // 4 key blocks of [128 rows x 64 keys] per group
 constexpr int A2_SMEM = 2 * A2_Q_BYTES + 2 * A2_KV_MAIN + 2 * A2_P_BYTES + 256 + 1024;   // Q tile double-buffered
 constexpr int A2_THREADS = 320;
-constexpr int A2_DEFAULT_VARIANT = 2 | 4;      // see attention_tc2_set_variant; chosen by profiles/r02l_*, r02m_*
 
-// max of one 32-column chunk of scores; columns past `lim` (causal mask / sequence end) do not count
-template <bool FAST>
-__device__ __forceinline__ float a2_chunk_max(const uint32_t (&v)[32], int lim) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-  // FAST: an unmasked copy of the loop for chunks no lane has to mask (warp-uniform: a per-lane branch would run both
-  // copies on the causal diagonal)
-  if (FAST && __all_sync(0xffffffffu, lim >= 31)) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      m0 = fmaxf(m0, __uint_as_float(v[j + 0]));
-      m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-      m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
-      m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
-      m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
-      m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
-      m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
-    }
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
-
-// p = 2^(s * scale_log2e - mb) of one chunk, summed into l0 / l1 and written as bf16 into row r of the group's
-// swizzled K-major P tile (chunk c = columns 32c .. 32c + 31 = half of a 64-key block)
-template <bool FAST>
-__device__ __forceinline__ void a2_chunk_exp(const uint32_t (&v)[32], int lim, float scale_log2e, float mb, float& l0, float& l1,
-                                             uint8_t* sPg, int c, int r) {
-  uint32_t pk[16];
-  if (FAST && __all_sync(0xffffffffu, lim >= 31)) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float p0, p1;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
-      l0 += p0;
-      l1 += p1;
-      pk[j >> 1] = pack_bf16x2(p0, p1);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float p0, p1;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
-      p0 = j <= lim ? p0 : 0.f;
-      p1 = j + 1 <= lim ? p1 : 0.f;
-      l0 += p0;
-      l1 += p1;
-      pk[j >> 1] = pack_bf16x2(p0, p1);
-    }
-  }
-  uint8_t* blk = sPg + (c >> 1) * (128 * 128) + r * 128;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
-    *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
-  }
-}
-
-// PIPE: tcgen05.ld of the next chunk in flight while the current one is processed.  FAST: unmasked loop copies.
-template <bool PIPE, bool FAST>
 __global__ void __launch_bounds__(A2_THREADS, 1)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
+attention_tc2_r02i_kernel(const __grid_constant__ CUtensorMap tmBig,
                      const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int T, int heads,
-                     int w, float scale_log2e, int causal, int tail_external, int pv_gran) {
+                     int w, float scale_log2e, int causal) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -120,7 +53,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   uint64_t* v_full = bars + 6;
   uint64_t* v_free = bars + 7;
   uint64_t* s_full = bars + 8;    // [2]
-  uint64_t* p_full = bars + 17;   // [2 groups][4 key blocks of 64]: P columns of the block written by all 4 warps
+  uint64_t* p_full = bars + 10;   // [2]
   uint64_t* o_full = bars + 12;   // [2]
   uint64_t* buf_free = bars + 14; // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
@@ -129,10 +62,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   const int keys_main = T < 256 ? (T + 15) / 16 * 16 : 256;  // keys on the tensor core (multiple of 16)
   const int extra = T > 256 ? T - 256 : 0;                    // keys handled on the FMA pipe
   const int kv_boxes = (keys_main + 127) / 128;
-  const int key_blocks = (keys_main + 63) / 64;                // 64-key blocks of the P tile
-  // tail_external: the last T mod 128 query rows (1..4 of them, after at least one full tile) are computed by
-  // attention_tail_kernel next to this kernel instead of a padded 128-row tile of their own
-  const int q_tiles = tail_external ? T / 128 : (T + 127) / 128;
+  const int q_tiles = (T + 127) / 128;
   const int items = B * heads;
 
   if (warp == 8 && lane == 0) {
@@ -146,7 +76,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         // keys past 256 are scored on the FMA pipe from the q rows in shared memory: the tile's softmax warps hold it too
         ptx::mbar_init(&q_empty[i], extra > 0 ? 5 : 1);
         ptx::mbar_init(&s_full[i], 1);
-        for (int kb = 0; kb < 4; kb++) ptx::mbar_init(&p_full[i * 4 + kb], 4);
+        ptx::mbar_init(&p_full[i], 4);
         ptx::mbar_init(&o_full[i], 1);
         ptx::mbar_init(&buf_free[i], 4);
       }
@@ -199,40 +129,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
       uint32_t prev_tc = 0;
       bool prev_last = false, prev_first = false;
       uint32_t prev_it = 0;
-      // The issuer is ONE thread and every instruction in front of a tcgen05.mma is serial latency on the path
-      // softmax -> P.V -> read-out.  With the descriptors rebuilt from addresses inside the loops the 16 P.V MMAs of a
-      // tile took ~20 uniform-datapath instructions each (SASS of the session-i build): the P.V phase was issue-bound,
-      // not tensor-bound.  Here the four base descriptors are built once and every MMA adds a compile-time constant.
-      const uint64_t dq_base = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ));
-      const uint64_t dk_base = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
-      const uint64_t dv_base = ptx::umma_desc_k_sw128(ptx::smem_u32(sV));
-      const uint64_t dp_base = ptx::umma_desc_k_sw128(ptx::smem_u32(sP));
-      const int nks = keys_main / 16;
       auto issue_pv = [&](uint32_t ptc, bool first_of_item, bool last_of_item, uint32_t pit) {
         const int pb = ptc & 1;
         if (first_of_item) ptx::mbar_wait(v_full, pit & 1);
-        const uint64_t dp0 = dp_base + (uint64_t)(pb * (A2_P_BYTES >> 4));
-        const uint32_t td = tmem_base + pb * 256;
-        const uint32_t par = (ptc >> 1) & 1;
-        // P.V follows the softmax in groups of pv_gran (1, 2 or 4) 64-key blocks: it starts when the first group of P is
-        // in shared memory, and when the last exponential is written only the last group's MMAs remain in front of the
-        // read-out.  (O lands in columns 0..63 of the tile's own S buffer: block 0 complete means every warp is past
-        // those columns.)
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) {
-          if (kb < key_blocks) {
-            if ((kb & (pv_gran - 1)) == 0) {
-              ptx::mbar_wait(&p_full[pb * 4 + min(kb + pv_gran, key_blocks) - 1], par);   // this group of P is in shared memory
-              ptx::tc_fence_after();
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int ks = kb * 4 + j;
-              if (ks < nks)
-                ptx::umma_f16(td, dp0 + (uint64_t)(kb * ((128 * 128) >> 4) + j * 2), dv_base + (uint64_t)(ks * ((16 * 128) >> 4)),
-                              idesc_o, ks != 0 ? 1u : 0u);   // 16 keys of V = 2 swizzle atoms of 8 rows
-            }
-          }
+        ptx::mbar_wait(&p_full[pb], (ptc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint8_t* sPg = sP + pb * A2_P_BYTES;
+        for (int ks = 0; ks < keys_main / 16; ks++) {
+          const uint64_t dp = ptx::umma_desc_k_sw128(ptx::smem_u32(sPg + (ks >> 2) * (128 * 128))) + (uint64_t)((ks & 3) * 2);
+          const uint64_t dv = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + ks * 16 * 128));  // 16 keys = 2 swizzle atoms
+          ptx::umma_f16(tmem_base + pb * 256, dp, dv, idesc_o, ks != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&o_full[pb]);
         if (last_of_item) ptx::umma_commit(v_free);
@@ -244,10 +150,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
           ptx::mbar_wait(&q_full[bsel], (tc >> 1) & 1);
           ptx::mbar_wait(&buf_free[bsel], ((tc >> 1) & 1) ^ 1);   // O(tc-2) has been read out of this buffer
           ptx::tc_fence_after();
-          const uint64_t dq = dq_base + (uint64_t)(bsel * (A2_Q_BYTES >> 4));
+          const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ + bsel * A2_Q_BYTES));
+          const uint64_t dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
 #pragma unroll
           for (int k = 0; k < A2_HD / 16; k++)
-            ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk_base + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+            ptx::umma_f16(tmem_base + bsel * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
           ptx::umma_commit(&q_empty[bsel]);
           ptx::umma_commit(&s_full[bsel]);
           if (mt == q_tiles - 1) ptx::umma_commit(k_free);
@@ -287,8 +194,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
           ptx::fence_proxy_async();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0)
-            for (int g0 = 0; g0 < key_blocks; g0 += pv_gran) ptx::mbar_arrive(&p_full[grp * 4 + min(g0 + pv_gran, key_blocks) - 1]);
+          if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
           ptx::mbar_wait(&o_full[grp], n & 1);
           ptx::tc_fence_after();
           ptx::tc_fence_before();
@@ -336,71 +242,52 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
         }
         ptx::mbar_wait(&s_full[grp], n & 1);
         ptx::tc_fence_after();
-        // pass 1: row maximum.  The TMEM loads are software-pipelined over two register buffers: tcgen05.ld of chunk
-        // c + 1 is in flight while chunk c is reduced (a wait::ld right behind every load left the warp idle for the
-        // whole TMEM round trip 16 times per tile; with two softmax warps per scheduler nothing else filled the gap).
+        // pass 1: row maximum
         float m = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 8; e++) m = fmaxf(m, se[e]);
-        uint32_t va[32], vb[32];
-        if constexpr (PIPE) {
-          ptx::tmem_ld_32x32b_x32(tbase, va);
 #pragma unroll 1
-          for (int c = 0; c < chunks; c += 2) {
-            ptx::tmem_ld_wait();
-            if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
-            m = fmaxf(m, a2_chunk_max<FAST>(va, kmax - c * 32));
-            if (c + 1 < chunks) {
-              ptx::tmem_ld_wait();
-              if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
-              m = fmaxf(m, a2_chunk_max<FAST>(vb, kmax - (c + 1) * 32));
-            }
+        for (int c = 0; c < chunks; c++) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+          ptx::tmem_ld_wait();
+          const int lim = kmax - c * 32;
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, j + 0 <= lim ? __uint_as_float(v[j + 0]) : -INFINITY);
+            m1 = fmaxf(m1, j + 1 <= lim ? __uint_as_float(v[j + 1]) : -INFINITY);
+            m2 = fmaxf(m2, j + 2 <= lim ? __uint_as_float(v[j + 2]) : -INFINITY);
+            m3 = fmaxf(m3, j + 3 <= lim ? __uint_as_float(v[j + 3]) : -INFINITY);
           }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < chunks; c++) {
-            ptx::tmem_ld_32x32b_x32(tbase + c * 32, va);
-            ptx::tmem_ld_wait();
-            m = fmaxf(m, a2_chunk_max<FAST>(va, kmax - c * 32));
-          }
+          m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         }
-        // pass 2: exponentials, row sum, P -> swizzled K-major tile of this group (same pipelining); after every
-        // 64-key block this warp's 32 rows of the block are handed to the tensor core
+        // pass 2: exponentials, row sum, P -> swizzled K-major tile of this group
         const float mb = m * scale_log2e;
         float l0 = 0.f, l1 = 0.f;
-        if constexpr (PIPE) {
-          ptx::tmem_ld_32x32b_x32(tbase, va);
 #pragma unroll 1
-          for (int c = 0; c < chunks; c += 2) {
-            ptx::tmem_ld_wait();
-            if (c + 1 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
-            a2_chunk_exp<FAST>(va, kmax - c * 32, scale_log2e, mb, l0, l1, sPg, c, r);
-            if (c + 1 < chunks) {
-              ptx::tmem_ld_wait();
-              if (c + 2 < chunks) ptx::tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
-              a2_chunk_exp<FAST>(vb, kmax - (c + 1) * 32, scale_log2e, mb, l0, l1, sPg, c + 1, r);
-            }
-            const int kb = c >> 1;
-            if (((kb + 1) & (pv_gran - 1)) == 0 || kb == key_blocks - 1) {
-              ptx::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&p_full[grp * 4 + kb]);
-            }
+        for (int c = 0; c < chunks; c++) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c * 32, v);
+          ptx::tmem_ld_wait();
+          const int lim = kmax - c * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[j]), scale_log2e, -mb)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mb)));
+            p0 = j <= lim ? p0 : 0.f;
+            p1 = j + 1 <= lim ? p1 : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
           }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < chunks; c++) {
-            ptx::tmem_ld_32x32b_x32(tbase + c * 32, va);
-            ptx::tmem_ld_wait();
-            a2_chunk_exp<FAST>(va, kmax - c * 32, scale_log2e, mb, l0, l1, sPg, c, r);
-            const int kb = c >> 1;
-            if (((c & 1) || c == chunks - 1) && (((kb + 1) & (pv_gran - 1)) == 0 || kb == key_blocks - 1)) {
-              ptx::fence_proxy_async();
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&p_full[grp * 4 + kb]);
-            }
+          uint8_t* blk = sPg + (c >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int ch = (((c & 1) * 4 + i) ^ (r & 7)) * 16;
+            *reinterpret_cast<uint4*>(blk + ch) = make_uint4(pk[i * 4], pk[i * 4 + 1], pk[i * 4 + 2], pk[i * 4 + 3]);
           }
         }
         float pe[8];
@@ -412,6 +299,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
           l0 += pe[e];
         }
         const float l = l0 + l1;
+        ptx::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
         // output: O from TMEM (+ the extra keys' p_e * v_e), * 1/l, bf16
         ptx::mbar_wait(&o_full[grp], n & 1);
         ptx::tc_fence_after();
@@ -462,71 +353,27 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmBig,
   if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-// Softmax-loop variant (bit 0: pipelined tcgen05.ld, bit 1: unmasked loop copies, bit 2 / bit 3: P.V issued per 64 / 128 keys);
-// B200_ATTN_VARIANT overrides the default, attention_tc2_set_variant() switches at run time (A/B in one process).
-static int a2_default_variant() {
-  const char* e = getenv("B200_ATTN_VARIANT");
-  return e ? atoi(e) & 15 : A2_DEFAULT_VARIANT;
-}
-static std::atomic<int> g_a2_variant{a2_default_variant()};
-int attention_tc2_set_variant(int v) {
-  const int old = g_a2_variant.load();
-  if (v >= 0) g_a2_variant.store(v & 15);
-  return old;
-}
-
-bool attention_tc2_supported(int T, int heads, int w) {
+bool attention_tc2_r02i_supported(int T, int heads, int w) {
   return heads > 0 && w % heads == 0 && w / heads == A2_HD && T >= 1 && T <= A2_MAXT;
 }
 
-int attention_tc2(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
-                  int causal, int sms, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join, int tail_mode) {
-  B200_CHECK(attention_tc2_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc2: unsupported shape T=%d hd=%d", T,
+int attention_tc2_r02i(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
+                  int causal, int sms, cudaStream_t st) {
+  B200_CHECK(attention_tc2_r02i_supported(T, heads, w), B200_ERR_UNSUPPORTED, "attention_tc2: unsupported shape T=%d hd=%d", T,
              heads ? w / heads : 0);
   if (B == 0) return B200_OK;
   static std::atomic<unsigned long long> configured{0};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!(configured.load() >> (dev & 63) & 1ull)) {
-    B200_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(attention_tc2_r02i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
     configured.fetch_or(1ull << (dev & 63));
   }
   const float scale_log2e = (1.0f / sqrtf((float)A2_HD)) * 1.4426950408889634f;
   const int items = B * heads;
   const int grid = items < sms ? items : sms;
-  // T = 257: two full tiles on the tensor cores and ONE leftover row.  As a third 128-row tile that row costs
-  // 0.36 ms per ViT-L/14 layer at batch 1024 (T = 256: 0.769 ms, T = 257: 1.131 ms).  Moving it to a small kernel on a
-  // second stream was measured and LOSES (1.391 ms stand-alone, attention 38.1 -> 43.1 ms per step in the model,
-  // profiles/r02j_attention_tail_ab.txt): the warp-per-row kernel re-reads K and V of its head from L2 for one row
-  // (0.45 ms on its own) and competes with the tensor-core kernel for the same SMs.  Kept behind
-  // B200_ATTN_TAIL_KERNEL=1 for the record; the default computes every row on the tensor cores.
-  static const bool tail_on = getenv("B200_ATTN_TAIL_KERNEL") != nullptr && atoi(getenv("B200_ATTN_TAIL_KERNEL")) != 0;
-  const int variant = g_a2_variant.load();
-  // 64-key blocks of P per hand-over to the tensor core: 1 (bit 2), 2 (bit 3), else 4 = the whole tile at once.  Short
-  // sequences (text, 77 tokens = 2 blocks, one query tile per head) have nothing to overlap an early P.V with: one hand-over.
-  const int key_blocks = ((T < 256 ? (T + 15) / 16 * 16 : 256) + 63) / 64;
-  const int pv_gran = key_blocks <= 2 ? 4 : (variant & 4) ? 1 : (variant & 8) ? 2 : 4;
-  const int n_full = T / 128, rem = T - n_full * 128;
-  const bool external = (tail_mode < 0 ? tail_on : tail_mode != 0) && side != nullptr && ev_fork != nullptr && ev_join != nullptr && rem > 0 && rem <= 4 && n_full >= 1;
-  if (external) {
-    B200_CUDA(cudaEventRecord(ev_fork, st));
-    B200_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    B200_TRY(attention_tail_rows(qkv, out, B, T, heads, w, causal, n_full * 128, rem, side));
-    B200_CUDA(cudaEventRecord(ev_join, side));
-  }
-  auto kern = attention_tc2_kernel<false, false>;
-  switch (variant & 3) {
-    case 1: kern = attention_tc2_kernel<true, false>; break;
-    case 2: kern = attention_tc2_kernel<false, true>; break;
-    case 3: kern = attention_tc2_kernel<true, true>; break;
-    default: break;
-  }
-  kern<<<grid, A2_THREADS, A2_SMEM, st>>>(tmBig, qkv, out, B, T, heads, w, scale_log2e, causal, external ? 1 : 0, pv_gran);
+  attention_tc2_r02i_kernel<<<grid, A2_THREADS, A2_SMEM, st>>>(tmBig, qkv, out, B, T, heads, w, scale_log2e, causal);
   B200_LAUNCH_OK();
-  if (external) B200_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   return B200_OK;
 }
 

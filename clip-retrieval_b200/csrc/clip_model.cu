@@ -19,6 +19,8 @@
 #include <cstdlib>
 
 namespace b200 {
+int attention_tc2_r02i(const CUtensorMap& tmBig, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int heads, int w,
+                       int causal, int sms, cudaStream_t st);
 
 struct Linear {
   __nv_bfloat16* w = nullptr;  // [N, K]
@@ -244,8 +246,10 @@ static int run_blocks(b200_clip* m, Tower& t, int B, int causal, cudaStream_t st
     { SpanGuard sg(m, CLS_ATTN, st); m->last_launches++;
       if (t.use_tc_attn && m->attn_gen == 3 && attention_tc3_supported(t.T, t.heads, w))
         B200_TRY(attention_tc3(t.tm_qkv3, t.qkv, t.a, t.kmax, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join));
-      else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w))
-        B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join));
+      else if (t.use_tc_attn && m->attn_pipelined && attention_tc2_supported(t.T, t.heads, w)) {
+        if (m->attn_gen == 4) { B200_TRY(attention_tc2_r02i(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st)); }
+        else { B200_TRY(attention_tc2(t.tm_qk, t.qkv, t.a, B, t.T, t.heads, w, causal, m->sms, st, m->s_side, m->ev_fork, m->ev_join)); }
+      }
       else if (t.use_tc_attn) B200_TRY(attention_tc(t.tm_qk, t.tm_vt, t.a, B, t.T, t.heads, w, causal, m->attn_v_direct ? 1 : 0, m->sms, st));
       else B200_TRY(attention(t.qkv, t.a, B, t.T, t.heads, w, causal, st)); }
     GemmEpilogue e2; e2.out = t.x; e2.out_ld = w; e2.residual = t.x; e2.res_ld = w;
@@ -752,6 +756,10 @@ int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, v
     return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
                          (cudaStream_t)stream, side[d], ev[d][0], ev[d][1], 1);
   }
+  // Tp == -4: the round-2 session-i build of attention_tc2 (A/B reference for one measurement session)
+  if (Tp == -4)
+    return attention_tc2_r02i(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),
+                              (cudaStream_t)stream);
   // Tp < 0: the two-tiles-in-flight kernel (attention_tc2.cu), every row on the tensor cores
   if (Tp < 0)
     return attention_tc2(tq, (const __nv_bfloat16*)d_qkv, (__nv_bfloat16*)d_out, B, T, heads, w, causal, sm_count(device),

@@ -93,12 +93,31 @@ int gemm_pick_bn(int M, int N, int sms) {
   return 256;
 }
 
-template <int BN>
-static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                     int sms, cudaStream_t st) {
+// TMA-store pair kernel with the epilogue flavour fixed at compile time (epi_pack8): activation | residual << 2
+typedef void (*pair_kernel_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, GemmEpilogue);
+static pair_kernel_fn pair_spec_kernel(int spec) {
+  switch (spec) {
+    case 0: return gemm_bf16_tcgen05_pair_kernel<true, 0>;
+    case 1: return gemm_bf16_tcgen05_pair_kernel<true, 1>;
+    case 2: return gemm_bf16_tcgen05_pair_kernel<true, 2>;
+    case 4: return gemm_bf16_tcgen05_pair_kernel<true, 4>;
+    case 5: return gemm_bf16_tcgen05_pair_kernel<true, 5>;
+    case 6: return gemm_bf16_tcgen05_pair_kernel<true, 6>;
+    default: return nullptr;
+  }
+}
+static bool gemm_pair_spec_default() {
+  const char* e = getenv("B200_GEMM_SPEC");
+  return e ? atoi(e) != 0 : true;
+}
+static bool g_pair_spec = gemm_pair_spec_default();   // B200_GEMM_SPEC=0: the generic run-time epilogue (A/B, parity)
+
+template <int BN, int SPEC>
+static int launch_bn_spec(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                          int sms, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static std::atomic<unsigned long long> configured{0};  // bit per device: the attribute is per context
-  auto kern = gemm_bf16_tcgen05_kernel<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, SPEC>;
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!(configured.load() >> (dev & 63) & 1ull)) {
@@ -110,6 +129,27 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep);
   B200_LAUNCH_OK();
   return B200_OK;
+}
+
+// single-CTA kernels: the epilogue flavour (activation | residual << 2) fixed at compile time unless the LayerNorm fold,
+// the row statistics or the transposed-V output are in use
+template <int BN>
+static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                     int sms, cudaStream_t st) {
+  const bool plain = g_pair_spec && ep.ln_stats == nullptr && ep.stats_out == nullptr && ep.ln_c == nullptr && ep.vt == nullptr &&
+                     ep.act >= 0 && ep.act <= 2;
+  if (plain) {
+    switch ((ep.act & 3) | (ep.residual ? 4 : 0)) {
+      case 0: return launch_bn_spec<BN, 0>(tmA, tmB, M, N, K, ep, sms, st);
+      case 1: return launch_bn_spec<BN, 1>(tmA, tmB, M, N, K, ep, sms, st);
+      case 2: return launch_bn_spec<BN, 2>(tmA, tmB, M, N, K, ep, sms, st);
+      case 4: return launch_bn_spec<BN, 4>(tmA, tmB, M, N, K, ep, sms, st);
+      case 5: return launch_bn_spec<BN, 5>(tmA, tmB, M, N, K, ep, sms, st);
+      case 6: return launch_bn_spec<BN, 6>(tmA, tmB, M, N, K, ep, sms, st);
+      default: break;
+    }
+  }
+  return launch_bn_spec<BN, -1>(tmA, tmB, M, N, K, ep, sms, st);
 }
 
 int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int M, int N, int K,
@@ -134,6 +174,8 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
                                      G2Cfg<false>::SMEM_BYTES));
       B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      G2Cfg<true>::SMEM_BYTES));
+      for (int spec = 0; spec < 8; spec++)
+        if (pair_spec_kernel(spec)) B200_CUDA(cudaFuncSetAttribute(pair_spec_kernel(spec), cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<true>::SMEM_BYTES));
       configured.fetch_or(1ull << (dev & 63));
     }
     const long tiles = (long)((M + G2_BM - 1) / G2_BM) * ((N + G2_BN - 1) / G2_BN);
@@ -143,8 +185,13 @@ int gemm_bf16_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int
     if (tma_st) {
       GemmEpilogue e2 = ep;
       e2.tma_store = 1;
-      gemm_bf16_tcgen05_pair_kernel<true><<<2 * pairs, GEMM_THREADS, G2Cfg<true>::SMEM_BYTES, st>>>(
-          tmA, tmB, *tmC, ep.residual ? *tmR : *tmC, M, N, K, e2);
+      // the epilogue flavour fixed at compile time whenever the LayerNorm fold / row statistics are off (always, by default)
+      const int spec = (ep.act & 3) | (ep.residual ? 4 : 0);
+      pair_kernel_fn kern = gemm_bf16_tcgen05_pair_kernel<true>;
+      if (g_pair_spec && ep.ln_stats == nullptr && ep.stats_out == nullptr && ep.ln_c == nullptr && ep.act >= 0 && ep.act <= 2 &&
+          pair_spec_kernel(spec) != nullptr)
+        kern = pair_spec_kernel(spec);
+      kern<<<2 * pairs, GEMM_THREADS, G2Cfg<true>::SMEM_BYTES, st>>>(tmA, tmB, *tmC, ep.residual ? *tmR : *tmC, M, N, K, e2);
     } else {
       gemm_bf16_tcgen05_pair_kernel<false><<<2 * pairs, GEMM_THREADS, G2Cfg<false>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, M, N, K, ep);
     }
@@ -205,18 +252,28 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
   static const bool dbg_on = getenv("B200_GEMM_DEBUG") != nullptr;
   if (dbg_on && bn == GEMM_MODE_PAIR) {
     unsigned long long* d = nullptr;
-    B200_CUDA(cudaMalloc((void**)&d, 32));
-    B200_CUDA(cudaMemsetAsync(d, 0, 32, (cudaStream_t)stream));
+    B200_CUDA(cudaMalloc((void**)&d, 64));
+    B200_CUDA(cudaMemsetAsync(d, 0, 64, (cudaStream_t)stream));
     ep.dbg = d;
-    int rc = gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream, nullptr, nullptr);
-    unsigned long long h[4] = {0, 0, 0, 0};
+    CUtensorMap dC, dR;
+    const bool maps = N >= 64;
+    if (maps) {
+      B200_TRY(make_tmap_2d(&dC, d_C, 1, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64));
+      if (d_residual) B200_TRY(make_tmap_2d(&dR, d_residual, 1, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64));
+    }
+    int rc = gemm_bf16_launch(tmA, tmB, bn, M, N, K, ep, sms, (cudaStream_t)stream, maps ? &dC : nullptr,
+                              maps && d_residual ? &dR : nullptr);
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    B200_CUDA(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost));
     cudaFree(d);
     const double pairs = sms / 2;
-    fprintf(stderr, "[gemm dbg] M=%d N=%d K=%d act=%d res=%d: issuer cycles/pair %.0f, wait operands %.1f%%, wait accumulator %.1f%%, producer wait-for-slot %.1f%%\n",
-            M, N, K, act, d_residual != nullptr, h[2] / pairs, 100.0 * h[0] / (double)h[2], 100.0 * h[1] / (double)h[2],
-            100.0 * h[3] / (double)h[2]);
+    const double tiles_per_pair = ((M + 255) / 256) * (double)((N + 255) / 256) / pairs;
+    fprintf(stderr, "[gemm dbg] M=%d N=%d K=%d act=%d res=%d: issuer cycles/pair %.0f (%.0f per tile), wait operands %.1f%%, wait accumulator %.1f%%, producer wait-for-slot %.1f%%"
+                    " | epilogue warp 0 of the leader, cycles per tile: before the accumulator wait %.0f, waiting for the accumulator %.0f, accumulator -> TMEM released %.0f, released -> end of tile %.0f\n",
+            M, N, K, act, d_residual != nullptr, h[2] / pairs, h[2] / pairs / tiles_per_pair, 100.0 * h[0] / (double)h[2], 100.0 * h[1] / (double)h[2],
+            100.0 * h[3] / (double)h[2], h[4] / pairs / tiles_per_pair, h[5] / pairs / tiles_per_pair, h[6] / pairs / tiles_per_pair,
+            h[7] / pairs / tiles_per_pair);
     return rc;
   }
   CUtensorMap tmC, tmR;
@@ -231,6 +288,7 @@ extern "C" int b200_gemm_bf16_device(const void* d_A, const void* d_W, const flo
 
 extern "C" int b200_gemm_set_tma_store(int on) {
   b200::gemm_set_tma_store(on != 0);
+  b200::g_pair_spec = on != 2;   // 2: TMA stores with the generic run-time epilogue (parity / A/B against the specialised ones)
   return B200_OK;
 }
 

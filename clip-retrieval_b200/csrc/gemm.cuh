@@ -58,7 +58,7 @@ struct GemmEpilogue {
   // Optional transposed store of the V third of a QKV projection (columns >= vt_col0): element
   // (row = b*T + t, col = vt_col0 + h*hd + dd) goes to vt[((b*heads + h)*hd + dd) * vt_Tp + t], i.e. V^T
   // per (sample, head) with keys contiguous — the K-major B operand of the P.V MMA (attention_tc.cu).
-  unsigned long long* dbg = nullptr;   // optional: [0] cycles the MMA issuer waited for operands, [1] for a free
+  unsigned long long* dbg = nullptr;   // optional (8 counters): [4..7] epilogue warp 0 per-tile phases; [0] cycles the MMA issuer waited for operands, [1] for a free
                                        // accumulator, [2] total issuer cycles, [3] producer waits for a free slot (pair kernel)
   int exp_b_bytes = 0;                 // timing experiment only (B200_GEMM_HALFB): bytes of B each CTA really loads per stage
   int exp_skip_tmem = 0;               // timing experiment only (B200_GEMM_NOLDTM): the epilogue does not read the accumulator
@@ -165,24 +165,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // otherwise sit in the middle of the epilogue: 57% of the stall samples in profiles/r01c).
 // s_bias = bias (or the folded LayerNorm's d), s_c = the folded LayerNorm's c (read only when ep.ln_stats is set).
 // st_k / st_s / st_q: running shifted sums of the stored values for the row statistics (ep.stats_out).
+// SPEC: see epi_pack8 below (-1 = every feature decided at run time; 0..7 = activation | residual << 2 at compile time).
+template <int SPEC>
 __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r8,
                                            const float* s_bias, const float* s_c, int col, int n0, const uint4& rr,
                                            float st_k, float& st_s, float& st_q) {
+  const int act = SPEC >= 0 ? (SPEC & 3) : ep.act;
+  const bool use_ln = SPEC < 0 && ep.ln_stats != nullptr;
+  const bool use_stats = SPEC < 0 && ep.stats_out != nullptr;
+  const bool has_res = SPEC >= 0 ? ((SPEC >> 2) & 1) != 0 : er.res_ptr != nullptr;
   float v[8];
-  if (ep.ln_stats != nullptr) {
+  if (use_ln) {
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), ep.act);
+      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), act);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], act);
   }
-  if (er.res_ptr) {
+  if (has_res) {
     const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z), dd = unpack_bf16x2(rr.w);
-    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-    v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+    // __fadd_rn: never contracted with the activation's last multiply into an FMA — every epilogue flavour (run-time or
+    // compile-time, pair or single CTA) rounds the same way and stays bit-identical to the others
+    v[0] = __fadd_rn(v[0], a.x); v[1] = __fadd_rn(v[1], a.y); v[2] = __fadd_rn(v[2], b.x); v[3] = __fadd_rn(v[3], b.y);
+    v[4] = __fadd_rn(v[4], cc.x); v[5] = __fadd_rn(v[5], cc.y); v[6] = __fadd_rn(v[6], dd.x); v[7] = __fadd_rn(v[7], dd.y);
   }
-  if (er.vt_ptr != nullptr && n0 + col >= ep.vt_col0) {
+  if (SPEC < 0 && er.vt_ptr != nullptr && n0 + col >= ep.vt_col0) {
     __nv_bfloat16* p = er.vt_ptr + (int64_t)(n0 + col - ep.vt_col0) * ep.vt_Tp;
 #pragma unroll
     for (int j = 0; j < 8; j++) p[(int64_t)j * ep.vt_Tp] = __float2bfloat16_rn(v[j]);
@@ -199,7 +207,7 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow&
   } else
 #endif
   *reinterpret_cast<uint4*>(er.out_ptr + col) = o;
-  if (ep.stats_out != nullptr) {
+  if (use_stats) {
     // statistics of the values as stored (bf16), shifted by the slot's first value to keep the sums small
     const float2 f0 = unpack_bf16x2(o.x), f1 = unpack_bf16x2(o.y), f2 = unpack_bf16x2(o.z), f3 = unpack_bf16x2(o.w);
     const float e[8] = {f0.x - st_k, f0.y - st_k, f1.x - st_k, f1.y - st_k, f2.x - st_k, f2.y - st_k, f3.x - st_k, f3.y - st_k};
@@ -213,29 +221,40 @@ __device__ __forceinline__ void epi_store8(const GemmEpilogue& ep, const EpiRow&
 
 // The eight finished values of columns col..col+7 of this thread's row (bias / folded LayerNorm, activation, residual
 // given as 8 packed bf16 in `rr`), packed to bf16; optional row-statistics accumulation as in epi_store8.
+// SPEC >= 0 fixes the epilogue flavour at compile time (bits 0-1 activation, bit 2 residual; no LayerNorm fold, no row
+// statistics): the generic flavour (SPEC = -1) carries a run-time activation switch — two or three branches around
+// an inlined erff for EVERY element — plus the fold / statistics paths, 12 300 SASS instructions in the pair kernel, and
+// its epilogue took ~11 000 cycles per 128x256 tile against 8 192 for the MMAs of a K = 1024 tile (B200_GEMM_DEBUG,
+// profiles/r02o_gemm_epilogue_phases.txt): the K = 1024 GEMMs were bound by instruction fetch and branches.
+template <int SPEC>
 __device__ __forceinline__ uint4 epi_pack8(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r8, const float* s_bias,
                                            const float* s_c, int col, bool has_res, const uint4& rr, float st_k, float& st_s,
                                            float& st_q) {
+  const int act = SPEC >= 0 ? (SPEC & 3) : ep.act;
+  const bool use_ln = SPEC < 0 && ep.ln_stats != nullptr;
+  const bool use_stats = SPEC < 0 && ep.stats_out != nullptr;
   float v[8];
-  if (ep.ln_stats != nullptr) {
+  if (use_ln) {
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), ep.act);
+      v[j] = act_apply(fmaf(__uint_as_float(r8[j]), er.ln_a, fmaf(er.ln_b, s_c[col + j], s_bias[col + j])), act);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], ep.act);
+    for (int j = 0; j < 8; j++) v[j] = act_apply(__uint_as_float(r8[j]) + s_bias[col + j], act);
   }
   if (has_res) {
     const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y), cc = unpack_bf16x2(rr.z), dd = unpack_bf16x2(rr.w);
-    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-    v[4] += cc.x; v[5] += cc.y; v[6] += dd.x; v[7] += dd.y;
+    // __fadd_rn: never contracted with the activation's last multiply into an FMA — every epilogue flavour (run-time or
+    // compile-time, pair or single CTA) rounds the same way and stays bit-identical to the others
+    v[0] = __fadd_rn(v[0], a.x); v[1] = __fadd_rn(v[1], a.y); v[2] = __fadd_rn(v[2], b.x); v[3] = __fadd_rn(v[3], b.y);
+    v[4] = __fadd_rn(v[4], cc.x); v[5] = __fadd_rn(v[5], cc.y); v[6] = __fadd_rn(v[6], dd.x); v[7] = __fadd_rn(v[7], dd.y);
   }
   uint4 o;
   o.x = pack_bf16x2(v[0], v[1]);
   o.y = pack_bf16x2(v[2], v[3]);
   o.z = pack_bf16x2(v[4], v[5]);
   o.w = pack_bf16x2(v[6], v[7]);
-  if (ep.stats_out != nullptr) {
+  if (use_stats) {
     const float2 f0 = unpack_bf16x2(o.x), f1 = unpack_bf16x2(o.y), f2 = unpack_bf16x2(o.z), f3 = unpack_bf16x2(o.w);
     const float e[8] = {f0.x - st_k, f0.y - st_k, f1.x - st_k, f1.y - st_k, f2.x - st_k, f2.y - st_k, f3.x - st_k, f3.y - st_k};
 #pragma unroll
@@ -249,10 +268,12 @@ __device__ __forceinline__ uint4 epi_pack8(const GemmEpilogue& ep, const EpiRow&
 
 // One 32-column chunk `c` of the tile for this thread's row: the four 8-column groups, and (stats_out) the
 // (mean, M2) record of a completed 64-column slot (chunks 2j, 2j+1).
+template <int SPEC>
 __device__ __forceinline__ void epi_chunk(const GemmEpilogue& ep, const EpiRow& er, const uint32_t* r, const float* s_bias,
                                           const float* s_c, int c, int n0, int N, int row, const uint4* res4, float& st_k,
                                           float& st_s, float& st_q) {
-  if (ep.stats_out != nullptr && (c & 1) == 0) {
+  const bool use_stats = SPEC < 0 && ep.stats_out != nullptr;
+  if (use_stats && (c & 1) == 0) {
     // shift = what the first column of the slot will store (bf16): recomputed here, cheap
     st_s = 0.f;
     st_q = 0.f;
@@ -260,22 +281,22 @@ __device__ __forceinline__ void epi_chunk(const GemmEpilogue& ep, const EpiRow& 
     const int col = c * 32;
     if (ep.ln_stats != nullptr) v0 = act_apply(fmaf(__uint_as_float(r[0]), er.ln_a, fmaf(er.ln_b, s_c[col], s_bias[col])), ep.act);
     else v0 = act_apply(__uint_as_float(r[0]) + s_bias[col], ep.act);
-    if (er.res_ptr) v0 += unpack_bf16x2(res4[0].x).x;
+    if (er.res_ptr) v0 = __fadd_rn(v0, unpack_bf16x2(res4[0].x).x);
     st_k = __bfloat162float(__float2bfloat16_rn(v0));
   }
 #pragma unroll
   for (int g = 0; g < 4; g++) {
     const int col = c * 32 + g * 8;
-    if (n0 + col < N) epi_store8(ep, er, r + g * 8, s_bias, s_c, col, n0, res4[g], st_k, st_s, st_q);
+    if (n0 + col < N) epi_store8<SPEC>(ep, er, r + g * 8, s_bias, s_c, col, n0, res4[g], st_k, st_s, st_q);
   }
-  if (ep.stats_out != nullptr && (c & 1) == 1 && n0 + c * 32 < N) {
+  if (use_stats && (c & 1) == 1 && n0 + c * 32 < N) {
     const float mean = st_k + st_s * (1.0f / 64.0f);
     const float m2 = fmaxf(st_q - st_s * st_s * (1.0f / 64.0f), 0.f);
     ep.stats_out[(int64_t)row * (N >> 6) + ((n0 + c * 32) >> 6)] = make_float2(mean, m2);
   }
 }
 
-template <int BN>
+template <int BN, int SPEC = -1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                          int K, GemmEpilogue ep) {
@@ -387,14 +408,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
       for (int j = et; j < BN; j += 256) {
         s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
-        s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
+        if (SPEC < 0) s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < M;
       EpiRow er = epi_row(ep, row, n0);
-      if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
+      if (SPEC < 0 && ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
       float st_k = 0.f, st_s = 0.f, st_q = 0.f;
       constexpr int CPW = BN >= 64 ? BN / 64 : 1;   // 32-column chunks per epilogue warp
       if (half * CPW * 32 >= BN) {
@@ -414,7 +435,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int g = 0; g < 4; g++) {
           const int col = (half * CPW + ci) * 32 + g * 8;
-          res[ci][g] = (row_ok && er.res_ptr != nullptr && n0 + col < N)
+          const bool want = SPEC >= 0 ? ((SPEC >> 2) & 1) != 0 : er.res_ptr != nullptr;
+          res[ci][g] = (row_ok && want && n0 + col < N)
                            ? *reinterpret_cast<const uint4*>(er.res_ptr + col) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
@@ -434,7 +456,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
         }
-        if (row_ok) epi_chunk(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
+        if (row_ok) epi_chunk<SPEC>(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -35,7 +35,8 @@ constexpr int G2_A_BYTES = 128 * GEMM_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = 128 * GEMM_BK * 2;   // 16 KB (half of the 256-wide B tile)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 
-template <bool TMAST>
+// SPEC: see epi_pack8 (gemm.cuh): -1 = every epilogue feature decided at run time, 0..7 = activation | residual << 2 fixed.
+template <bool TMAST, int SPEC = -1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M,
@@ -177,18 +178,20 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int m_blk, n_blk;
       gemm_tile_coords(tile, mb, nb, m_blk, n_blk);
       const int n0 = n_blk * G2_BN;
+      const bool prof = ep.dbg != nullptr && leader && warp == 0 && lane == 0;   // B200_GEMM_DEBUG: where this warp's tile time goes
+      const long long tp0 = prof ? clock64() : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
       for (int j = et; j < G2_BN; j += 256) {
         s_bias[j] = (ep.bias != nullptr && n0 + j < N) ? ep.bias[n0 + j] : 0.0f;
-        s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
+        if (SPEC < 0) s_c[j] = (ep.ln_c != nullptr && n0 + j < N) ? ep.ln_c[n0 + j] : 0.0f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 
       const int row = m_blk * G2_BM + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = row < M;
       EpiRow er = epi_row(ep, row, n0);
-      if (ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
+      if (SPEC < 0 && ep.ln_stats != nullptr && row_ok) ln_row_coeffs(ep.ln_stats + (int64_t)row * (ep.ln_w >> 6), ep.ln_w >> 6, ep.ln_w, er.ln_a, er.ln_b);
       float st_k = 0.f, st_s = 0.f, st_q = 0.f;
       constexpr int CPW = G2_BN / 64;   // 32-column chunks per epilogue warp
       if constexpr (TMAST) {
@@ -196,7 +199,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         uint8_t* stage = sStage + warp * 8192;                 // two boxes of 32 rows x 64 columns (128 B rows, swizzled)
         const int row0 = m_blk * G2_BM + (int)rank * 128 + q * 32;      // first row of this warp's slab
         const int col0 = n0 + half * 128;                                // first column of this warp's half tile
-        const bool has_res = ep.residual != nullptr;
+        const bool has_res = SPEC >= 0 ? ((SPEC >> 2) & 1) != 0 : ep.residual != nullptr;
+        const bool use_stats = SPEC < 0 && ep.stats_out != nullptr;
+        const bool use_ln = SPEC < 0 && ep.ln_stats != nullptr;
+        const int act = SPEC >= 0 ? (SPEC & 3) : ep.act;
         int out_row0 = row0, res_row0 = row0;
         if (ep.out_group > 0) out_row0 = (row0 / ep.out_group) * (ep.out_group + 1) + 1 + row0 % ep.out_group;
         if (ep.res_row_mod > 0) res_row0 = ep.res_row_off + row0 % ep.res_row_mod;
@@ -209,8 +215,11 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           ptx::tma_load_2d(stage, &tmR, &rbar[warp], col0, res_row0);
           ptx::tma_load_2d(stage + 4096, &tmR, &rbar[warp], col0 + 64, res_row0);
         }
+        const long long tp1 = prof ? clock64() : 0;
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after();
+        const long long tp2 = prof ? clock64() : 0;
+        long long tp3 = 0;
         if (has_res && row0 < M) ptx::mbar_wait(&rbar[warp], rphase);
         // the accumulator chunk c+1 is in flight (tcgen05.ld) while chunk c is finished and staged
         uint32_t rbuf[2][32];
@@ -229,17 +238,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               if (leader) ptx::mbar_arrive(&tempty[acc]);
               else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
             }
+            if (prof) tp3 = clock64();
           }
-          if (ep.stats_out != nullptr && (c & 1) == 0) {
+          if (use_stats && (c & 1) == 0) {
             st_s = 0.f;
             st_q = 0.f;
             float v0;
             const int colb = c * 32;
-            if (ep.ln_stats != nullptr) v0 = act_apply(fmaf(__uint_as_float(r[0]), er.ln_a, fmaf(er.ln_b, s_c[colb], s_bias[colb])), ep.act);
-            else v0 = act_apply(__uint_as_float(r[0]) + s_bias[colb], ep.act);
+            if (use_ln) v0 = act_apply(fmaf(__uint_as_float(r[0]), er.ln_a, fmaf(er.ln_b, s_c[colb], s_bias[colb])), act);
+            else v0 = act_apply(__uint_as_float(r[0]) + s_bias[colb], act);
             if (has_res) {
               const uint4 r0 = *reinterpret_cast<const uint4*>(stage + (ci >> 1) * 4096 + lane * 128 + ((((ci & 1) * 4) ^ (lane & 7)) * 16));
-              v0 += unpack_bf16x2(r0.x).x;
+              v0 = __fadd_rn(v0, unpack_bf16x2(r0.x).x);
             }
             st_k = __bfloat162float(__float2bfloat16_rn(v0));
           }
@@ -251,10 +261,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             uint4 rr = make_uint4(0u, 0u, 0u, 0u);
             if (has_res) rr = *reinterpret_cast<const uint4*>(slot);
             uint4 o = make_uint4(0u, 0u, 0u, 0u);                        // rows past M store zeros
-            if (row_ok && n0 + col < N) o = epi_pack8(ep, er, r + g * 8, s_bias, s_c, col, has_res, rr, st_k, st_s, st_q);
+            if (row_ok && n0 + col < N) o = epi_pack8<SPEC>(ep, er, r + g * 8, s_bias, s_c, col, has_res, rr, st_k, st_s, st_q);
             *reinterpret_cast<uint4*>(slot) = o;
           }
-          if (ep.stats_out != nullptr && (c & 1) == 1 && row_ok && n0 + c * 32 < N) {
+          if (use_stats && (c & 1) == 1 && row_ok && n0 + c * 32 < N) {
             const float mean = st_k + st_s * (1.0f / 64.0f);
             const float m2 = fmaxf(st_q - st_s * st_s * (1.0f / 64.0f), 0.f);
             ep.stats_out[(int64_t)row * (N >> 6) + ((n0 + c * 32) >> 6)] = make_float2(mean, m2);
@@ -268,6 +278,13 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               ptx::bulk_commit_group();
             }
           }
+        }
+        if (prof) {
+          const long long tp4 = clock64();
+          atomicAdd(ep.dbg + 4, (unsigned long long)(tp1 - tp0));
+          atomicAdd(ep.dbg + 5, (unsigned long long)(tp2 - tp1));
+          atomicAdd(ep.dbg + 6, (unsigned long long)(tp3 - tp2));
+          atomicAdd(ep.dbg + 7, (unsigned long long)(tp4 - tp3));
         }
         if (has_res && row0 < M) rphase ^= 1;
         acc ^= 1;
@@ -311,7 +328,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             else ptx::mbar_arrive_cluster(tempty0_remote + (uint32_t)acc * 8u);
           }
         }
-        if (row_ok) epi_chunk(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
+        if (row_ok) epi_chunk<SPEC>(ep, er, r, s_bias, s_c, c, n0, N, row, res[ci], st_k, st_s, st_q);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -233,8 +233,10 @@ int b200_gemm_bf16_device(const void* d_A, const void* d_W, const float* d_bias,
 /* Large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles) by default; 0 forces the
  * single-CTA 128x256 kernel for every shape (A/B measurements, parity between the two kernels). */
 int b200_gemm_set_pair_mode(int on);
-/* CTA-pair kernel only: 1 = results (and the residual operand) travel through shared memory and TMA tensor
- * stores / loads instead of per-thread 16-byte global stores / loads; 0 = the register path (A/B, parity tests). */
+/* CTA-pair kernel only: 1 (default) = results (and the residual operand) travel through shared memory and TMA tensor
+ * stores / loads, epilogue flavour (activation, residual) fixed at compile time; 2 = the same with every epilogue
+ * feature decided at run time; 0 = per-thread 16-byte global stores / loads (A/B, parity tests: all three are
+ * bit-identical). */
 int b200_gemm_set_tma_store(int on);
 /* attention_tc2 (head dim 64, T <= 264) softmax-loop variant, for A/B measurements and parity between the variants:
  * bit 0 = tcgen05.ld of the next 32-column chunk in flight while the current one is processed, bit 1 = unmasked loop

@@ -64,11 +64,15 @@ def test_gemm_matches_fp32_reference(M, N, K, act, bias, res):
     (20001, 1024, 1024, 0, True, True),    # out-proj: residual prefetched by TMA, stored in place of it
     (19000, 1000, 520, 2, True, True),     # N and K tails: boxes clipped by the tensor maps
     (40000, 768, 3072, 0, True, True),     # text c_proj shape class
+    (20001, 512, 1024, 0, True, False),    # plain bias epilogue (qkv)
+    (20001, 1024, 1024, 1, True, True),    # QuickGELU + residual
+    (20001, 1024, 512, 2, False, False),   # erf-GELU, no bias
 ])
 def test_pair_gemm_tma_store_equals_register_store(M, N, K, act, bias, res):
-    """The CTA-pair kernel's two epilogues (results through shared memory + TMA tensor stores vs per-thread stores)
-    compute the same values: bit-identical outputs, also when the output buffer IS the residual (in-place update of
-    the residual stream, as the model runs it)."""
+    """The CTA-pair kernel's three epilogues (per-thread stores; results through shared memory + TMA tensor stores with
+    the activation / residual flavour fixed at compile time; the same with every feature decided at run time) compute
+    the same values: bit-identical outputs, also when the output buffer IS the residual (in-place update of the
+    residual stream, as the model runs it)."""
     import torch
     from clip_retrieval_b200._lib import lib, check
 
@@ -80,7 +84,7 @@ def test_pair_gemm_tma_store_equals_register_store(M, N, K, act, bias, res):
     st = torch.cuda.current_stream().cuda_stream
     outs = []
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             check(lib.b200_gemm_set_tma_store(mode), "set_tma_store")
             out = R.clone() if res else torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
             check(lib.b200_gemm_bf16_device(A.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None,
@@ -91,6 +95,7 @@ def test_pair_gemm_tma_store_equals_register_store(M, N, K, act, bias, res):
         check(lib.b200_gemm_set_tma_store(1), "set_tma_store")    # the default
     assert not torch.isnan(outs[1].float()).any()
     assert torch.equal(outs[0], outs[1]), "max diff %g" % (outs[0].float() - outs[1].float()).abs().max().item()
+    assert torch.equal(outs[2], outs[1]), "specialised vs run-time epilogue: max diff %g" % (outs[2].float() - outs[1].float()).abs().max().item()
     ref = _ref(A, W, b, R, act)
     err = (outs[1].float() - ref).abs()
     assert bool((err <= ref.abs() * 2 ** -7 + 0.02).all()), "max err %g" % err.max().item()

@@ -1,3 +1,4 @@
+# SPEC_MODES: --spec-ab times the run-time epilogue against the compile-time flavours
 """Sustained (power-capped) throughput of the model's four GEMM shapes with and without their epilogue
 features: each configuration runs back to back for ~1.5 s after a 1 s warm-up of the same kernel, so the
 clocks are the ones the model sees, not burst clocks."""
@@ -68,6 +69,11 @@ for name, N, K, feats in (("qkv", 3072, 1024, [(1, 0, 0)]),
                           ("fc", 4096, 1024, [(1, 0, 0), (1, 0, 1)]),
                           ("c_proj", 1024, 4096, [(1, 1, 0)])):
     for bias, res, act in feats:
-        run(name, N, K, bias, res, act)
+        for mode in ((2, 1) if "--spec-ab" in sys.argv else (1,)):   # 2 = run-time epilogue, 1 = compile-time flavour (default)
+            lib.b200_gemm_set_tma_store(mode)
+            if "--spec-ab" in sys.argv:
+                print("  [epilogue %s]" % ("run-time" if mode == 2 else "compile-time"), end=" ")
+            run(name, N, K, bias, res, act)
+        lib.b200_gemm_set_tma_store(1)
     if "--cublas" in sys.argv:
         run_cublas(name, N, K)
