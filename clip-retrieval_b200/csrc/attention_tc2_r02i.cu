@@ -1,3 +1,9 @@
+// FROZEN MEASUREMENT REFERENCE — not a production path.  This is attention_tc2.cu as it stood in round-2 session i
+// (commit b1984e3), compiled into the same library under other symbol names so that a later build of the kernel can be
+// timed against it in ONE process on ONE box (boxes of the pool differ by more than the changes being measured):
+// tools/attn_variants.py ("old" column, profiles/r02o_*) through b200_attention_tc_bf16_device(Tp = -4), and
+// B200_ATTN_GEN=4 in the model.  Nothing selects it by default.
+//
 // K4 on tcgen05, two query tiles in flight (the production attention for head dim 64, T <= 264:
 // every CLIP tower at 224 px except H/14's vision tower).
 //
