@@ -28,3 +28,45 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_plumbing_helpers_drive_the_reference_runner(tmp_path):
+    """configs[0] helpers of bench.py on the CPU: the synthetic tokenizer ends every caption with the largest id (the
+    text tower pools at argmax), and a ClipMapper-contract callable driven by the reference's own Runner (baseline/_ref)
+    produces the writer's shard layout in the sampler's order."""
+    import numpy as np
+    import pytest
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    tok = bench.hashed_tokenizer(["a photo of object 3", "", "x " * 200])
+    assert tok.shape == (3, 77) and tok.dtype == torch.int64
+    assert all(int(row.argmax()) == int((row != 0).sum()) - 1 and int(row.max()) == 49407 and int(row[0]) == 49406 for row in tok)
+    if not os.path.isdir(bench.REF_INFERENCE):
+        pytest.skip("baseline/_ref (reference install) not in this tree")
+    from clip_retrieval_b200.model import make_preprocess
+
+    n, parts, bs, d = 10, 2, 4, 16
+    src = str(tmp_path / "images")
+    bench.make_plumbing_dataset(src, n)
+    calls = []
+
+    def fake_mapper(batch, img, txt):
+        b = batch["image_tensor"].shape[0] if img else batch["text_tokens"].shape[0]
+        calls.append((img, b))
+        # embedding = the sample's number taken from its file name / caption, so the order can be checked in the shards
+        keys = batch["image_filename"] if img else batch["text"]
+        ids = [int(os.path.basename(k).split(".")[0]) if img else int(k.split()[-1]) for k in keys]
+        e = np.repeat(np.asarray(ids, dtype=np.float16)[:, None], d, axis=1)
+        return {"image_embs": e if img else None, "text_embs": e if txt else None,
+                "image_filename": batch["image_filename"] if img else None, "text": batch["text"] if txt else None, "metadata": None}
+
+    sec = bench.run_reference_runner(src, str(tmp_path / "out"), fake_mapper, make_preprocess(224), bench.hashed_tokenizer, parts, bs)
+    assert sec >= 0 and sum(b for img, b in calls if img) == n and sum(b for img, b in calls if not img) == n
+    img, txt = bench.read_plumbing_output(str(tmp_path / "out"))
+    for shards in (img, txt):
+        assert len(shards) == parts and all(s.dtype == np.float16 and s.shape == (n // parts, d) for s in shards)
+        for p in range(parts):   # runner.Sampler: partition p holds samples p, p + parts, ...
+            assert list(shards[p][:, 0].astype(int)) == list(range(n))[p::parts]
