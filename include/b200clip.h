@@ -252,7 +252,11 @@ int b200_layernorm_bf16_device(const void* d_in, void* d_out, const float* d_gam
 int b200_attention_bf16_device(const void* d_qkv, void* d_out, int B, int T, int heads, int w, int causal,
                                int device, void* stream);
 /* tcgen05 attention (head dim 64, T <= 320): the Q and K thirds are read from d_qkv, V^T from d_vt
- * ([B*heads*64, Tp] bf16, keys contiguous, columns >= T zero) — the layout the QKV GEMM epilogue writes. */
+ * ([B*heads*64, Tp] bf16, keys contiguous, columns >= T zero) — the layout the QKV GEMM epilogue writes.
+ * d_vt == NULL selects the kernels that read V from d_qkv (MN-major operand); Tp then names the generation under test:
+ *   0  attention_tc (one tile in flight)      -1  attention_tc2 (production; variant: b200_attention_set_variant)
+ *  -2  attention_tc3                          -3  attention_tc2 + leftover-row kernel on a second stream
+ *  -4  the frozen session-i build of attention_tc2 (same-process A/B reference, profiles/r02o_*). */
 int b200_attention_tc_bf16_device(const void* d_qkv, const void* d_vt, int Tp, void* d_out, int B, int T, int heads,
                                   int w, int causal, int device, void* stream);
 
